@@ -1,0 +1,203 @@
+/*
+ * ncf_b200.h — C ABI of the B200-native NCF training / leave-one-out evaluation hot path.
+ *
+ * The reference (YonkaMayonkaZ/NCF) has no FFI: its hot path is stock PyTorch ops driven
+ * from Python.  This header is the boundary a maintainer would bind instead:
+ * plain pointers and sizes, no torch types.  Every entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in _host.  The library never
+ *    allocates persistent memory and never frees caller memory; scratch comes from the
+ *    caller through (workspace, workspace_bytes) sized by the *_workspace_bytes queries.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *    host synchronisation and is CUDA-graph capturable.
+ *  - Return value: 0 = OK, NCF_ERR_ARG (-1) bad argument, NCF_ERR_CUDA (-2) CUDA error,
+ *    NCF_ERR_WORKSPACE (-3) workspace too small.  ncf_last_error() returns a thread-local
+ *    message for the last failing call on this thread.
+ *  - There is no CPU fallback: without a CUDA device every compute entry returns NCF_ERR_CUDA.
+ *  - Tables are fp32 row-major [rows, dim]; Linear weights are [out, in] row-major (the
+ *    nn.Linear layout, reference src/ncf/models.py:24,34); indices are int64 (torch default).
+ */
+#ifndef NCF_B200_H
+#define NCF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCF_ABI_VERSION 1
+#define NCF_MAX_LAYERS 8
+
+#define NCF_OK 0
+#define NCF_ERR_ARG (-1)
+#define NCF_ERR_CUDA (-2)
+#define NCF_ERR_WORKSPACE (-3)
+
+/* model_type of reference src/ncf/models.py:5,30-33 ("NeuMF-end" and "NeuMF-pre" compute alike) */
+#define NCF_GMF 0
+#define NCF_MLP 1
+#define NCF_NEUMF 2
+
+/* Parameters of one NCF model (reference src/ncf/models.py:11-34).  mlp_dim = factor_num *
+ * 2^(num_layers-1); tower layer k maps width factor_num*2^(num_layers-k) -> half of it. */
+typedef struct NcfModel {
+  int32_t model_type;
+  int32_t factor_num;
+  int32_t num_layers;
+  int32_t mlp_dim;
+  int64_t user_num;
+  int64_t item_num;
+  float* embed_user_gmf; /* [user_num, factor_num]  embed_user_GMF.weight */
+  float* embed_item_gmf; /* [item_num, factor_num]  embed_item_GMF.weight */
+  float* embed_user_mlp; /* [user_num, mlp_dim]     embed_user_MLP.weight */
+  float* embed_item_mlp; /* [item_num, mlp_dim]     embed_item_MLP.weight */
+  float* mlp_w[NCF_MAX_LAYERS]; /* MLP_layers.{3k+1}.weight [out_k, in_k] */
+  float* mlp_b[NCF_MAX_LAYERS]; /* MLP_layers.{3k+1}.bias   [out_k]       */
+  float* predict_w;             /* predict_layer.weight [1, f | 2f]       */
+  float* predict_b;             /* predict_layer.bias   [1]               */
+} NcfModel;
+
+/* Gradients of one training step.  The embedding gradients live in zero-initialised buffers
+ * addressed like the tables (only touched rows are ever non-zero; the optimiser re-zeroes
+ * them) plus a list of the distinct rows touched since the last optimiser step — the
+ * deduplicated replacement of autograd's dense embedding grad (reference
+ * scripts/train_neumf.py:114).  Tower gradients are one flat buffer laid out
+ * [W_0, b_0, W_1, b_1, ..., W_{L-1}, b_{L-1}, predict_w, predict_b]. */
+typedef struct NcfGrads {
+  float* g_user_gmf;
+  float* g_item_gmf;
+  float* g_user_mlp;
+  float* g_item_mlp;
+  float* g_tower;         /* flat, ncf_tower_param_count() floats */
+  int32_t* user_flag;     /* [user_num] 0/1 */
+  int32_t* item_flag;     /* [item_num] 0/1 */
+  int64_t* user_list;     /* capacity >= max distinct users per optimiser step */
+  int64_t* item_list;
+  int32_t* touched_count; /* [2]: {n_user_rows, n_item_rows} */
+} NcfGrads;
+
+/* Adam state (reference optim.Adam defaults, scripts/train_neumf.py:90).  The reference Adam is
+ * DENSE: a row touched once keeps moving every later step through its momentum.  We update
+ * only touched rows and replay the skipped zero-gradient steps lazily (last_step per row), so
+ * results equal the dense update.  ncf_adam_flush() brings every row up to
+ * date before weights are read (evaluation, checkpoint). */
+typedef struct NcfAdamState {
+  float* m_user_gmf; float* v_user_gmf;
+  float* m_item_gmf; float* v_item_gmf;
+  float* m_user_mlp; float* v_user_mlp;
+  float* m_item_mlp; float* v_item_mlp;
+  float* m_tower;    float* v_tower;
+  int32_t* user_last_step; /* [user_num], 0 = never touched */
+  int32_t* item_last_step; /* [item_num] */
+  int64_t* step;           /* [1] device step counter (number of optimiser steps taken) */
+} NcfAdamState;
+
+typedef struct NcfAdamHyper {
+  float lr, beta1, beta2, eps;
+} NcfAdamHyper;
+
+/* ---- library ------------------------------------------------------------------------- */
+int ncf_version(void);
+const char* ncf_last_error(void);
+/* number of floats in the flat tower buffer for this shape */
+int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num, int32_t num_layers);
+
+/* ---- a1: observed-pair structure --------------------------------------------------------
+ * Replaces the dok_matrix fill loop of reference src/data/datasets.py:20-24 by a CSR with
+ * sorted columns: rowptr int64[user_num+1], col int32[P].  Duplicate pairs are kept.
+ * workspace: ncf_csr_workspace_bytes(P, user_num). */
+int64_t ncf_csr_workspace_bytes(int64_t P, int64_t user_num);
+int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, int64_t P, int64_t user_num,
+                  int64_t* rowptr, int32_t* col, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+
+/* ---- a2: negative sampler ---------------------------------------------------------------
+ * Replaces NCFData.ng_sample (reference src/data/datasets.py:53-69): for positive p and
+ * t < num_ng, out_neg_item[p*num_ng + t] is drawn uniformly from [0, item_num) and redrawn
+ * while (pos_user[p], j) is an observed pair.  Draw a of sample s = p_offset+p, t uses word
+ * a%4 of Philox4x32-10(counter = {s*num_ng+t (lo), (hi), a/4, epoch}, key = seed), mapped to an
+ * item by mulhi32(word, item_num).  p_offset lets shards sample disjoint global sample ids. */
+int ncf_sample_neg(const int64_t* rowptr, const int32_t* col, const int64_t* pos_user, int64_t P,
+                   int64_t p_offset, int32_t num_ng, int64_t item_num, uint64_t seed,
+                   uint64_t epoch, int64_t* out_neg_item, void* stream);
+
+/* ---- a3: epoch shuffle + batching ---------------------------------------------------------
+ * Replaces DataLoader(shuffle=True) over NCFData.__getitem__ (reference
+ * src/data/datasets.py:71-83, scripts/train_neumf.py:55): position q of the epoch stream holds
+ * sample perm(q), where perm is a keyed bijection of [0, S), S = P*(1+num_ng); sample s < P is
+ * positive s with label 1, sample s >= P is negative s-P with label 0 (positives-then-negatives
+ * order of datasets.py:68).  Writes positions [q_begin, q_begin+count). */
+int ncf_shuffle_epoch(const int64_t* pos_user, const int64_t* pos_item, const int64_t* neg_item,
+                      int64_t P, int32_t num_ng, uint64_t seed, uint64_t epoch, int64_t q_begin,
+                      int64_t count, int64_t* out_user, int64_t* out_item, float* out_label,
+                      void* stream);
+
+/* ---- a6: forward (inference) --------------------------------------------------------------
+ * Replaces NCF.forward (reference src/ncf/models.py:97-118): logits[b] for (user[b], item[b]). */
+int64_t ncf_forward_workspace_bytes(const NcfModel* m_host, int64_t B);
+int ncf_forward(const NcfModel* m_host, const int64_t* user, const int64_t* item, int64_t B,
+                float* logits, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- a7/a8: loss and its gradient w.r.t. the logits -----------------------------------------
+ * Replaces nn.BCEWithLogitsLoss (reference scripts/train_neumf.py:86,113) and, when
+ * teacher_logits != NULL, ResponseDistillation.combined_loss (reference
+ * src/distillation/base.py:40-50 + response.py:28-32):
+ *   loss = alpha * mean BCE(x, y) + (1-alpha) * mean (x - t)^2     (alpha ignored without teacher)
+ * Adds the batch loss to *loss_accum (double) and, if dlogit != NULL, writes dloss/dx. */
+int ncf_loss_grad(const float* logits, const float* label, const float* teacher_logits,
+                  float alpha, int64_t B, double* loss_accum, float* dlogit, void* stream);
+
+/* ---- a6+a7+a8+a9: fused training step (forward, loss, backward) --------------------------------
+ * Replaces `prediction = model(user,item); loss = criterion(...); loss.backward()` (reference
+ * scripts/train_neumf.py:112-114; with teacher_logits: scripts/train_student.py:154-155).
+ * Accumulates into g (which must be zero for a fresh step), adds the batch loss to *loss_accum,
+ * optionally writes the logits.  workspace: ncf_train_workspace_bytes(m, B). */
+int64_t ncf_train_workspace_bytes(const NcfModel* m_host, int64_t B);
+int ncf_train_step_grads(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* user,
+                         const int64_t* item, const float* label, const float* teacher_logits,
+                         float alpha, int64_t B, double* loss_accum, float* logits_out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- a9 alone: backward from a caller-supplied dloss/dlogit ---------------------------------------
+ * Replaces autograd's backward through NCF.forward (reference scripts/train_neumf.py:114) when the
+ * loss was computed elsewhere (e.g. by torch in an unmodified reference loop): recomputes the
+ * forward for the batch inside the fused kernel and accumulates the gradients into g. */
+int ncf_backward(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* user,
+                 const int64_t* item, const float* dlogit, int64_t B, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+
+/* ---- a10: optimisers --------------------------------------------------------------------------
+ * ncf_adam_step: optim.Adam(lr, betas=(0.9,0.999), eps=1e-8).step() (reference
+ * scripts/train_neumf.py:90,115) on the tower (dense) and on the touched rows (lazy, dense-
+ * equivalent); consumes and re-zeroes g, increments *s->step.
+ * ncf_adam_flush: replays pending zero-gradient steps for every row (call before reading weights).
+ * ncf_sgd_step: optim.SGD(lr).step() (reference scripts/train_neumf.py:88), no momentum. */
+int ncf_adam_step(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
+                  NcfAdamHyper h, void* stream);
+int ncf_adam_flush(const NcfModel* m_host, const NcfAdamState* s_host, NcfAdamHyper h,
+                   void* stream);
+int ncf_sgd_step(const NcfModel* m_host, const NcfGrads* g_host, float lr, void* stream);
+
+/* ---- a11: leave-one-out evaluation --------------------------------------------------------------
+ * Replaces metrics() (reference src/training/metrics.py:4-25).  scores is [n, C]; column 0 is the
+ * held-out positive (reference src/data/datasets.py:31-34).  Per user: topk_idx[k] = indices of the
+ * k largest scores in descending order, ties broken towards the LOWER candidate index; rank =
+ * position of candidate 0 in that order (or -1); hit = rank >= 0; ndcg = 1/log2(rank+2) or 0.
+ * Any of hit / rank / ndcg / topk_idx may be NULL.  Requires 1 <= k <= C <= 1024. */
+int ncf_eval_rank(const float* scores, int64_t n, int32_t C, int32_t k, uint8_t* hit,
+                  int32_t* rank, float* ndcg, int32_t* topk_idx, void* stream);
+/* Scores every user's C candidates with the model, then ranks as above.
+ * workspace: ncf_eval_workspace_bytes(m, n, C). */
+int64_t ncf_eval_workspace_bytes(const NcfModel* m_host, int64_t n, int32_t C);
+int ncf_eval_users(const NcfModel* m_host, const int64_t* users, const int64_t* cands, int64_t n,
+                   int32_t C, int32_t k, uint8_t* hit, int32_t* rank, float* ndcg,
+                   int32_t* topk_idx, float* scores_out, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCF_B200_H */

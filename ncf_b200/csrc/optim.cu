@@ -1,0 +1,351 @@
+// a10 optimisers.  Adam over the touched embedding rows only, numerically equivalent to the
+// reference's DENSE optim.Adam (scripts/train_neumf.py:90,115) through lazy replay of the skipped
+// zero-gradient steps; dense Adam over the (small) tower; plain SGD (train_neumf.py:88).
+// HBM-bound: one warp per touched row streams g, p, m, v once (read) and p, m, v, g (write).
+//
+// torch.optim.Adam single-tensor math (torch 2.11 optim/adam.py), per step t = 1, 2, ...:
+//   m <- m + (1-b1)(g - m);  v <- b2 v + (1-b2) g^2
+//   p <- p - (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// A row whose gradient is zero at step s still moves: m <- b1 m, v <- b2 v, same p update.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+// Zero-gradient steps replayed exactly per row.  The per-step term decays like
+// (b1/sqrt(b2))^j ~ 0.9005^j, so what is dropped beyond 160 steps is < 1e-7 of the first term.
+constexpr int kMaxReplay = 160;
+
+struct AdamConst {
+  float lr, b1, b2, eps, ln_b1, ln_b2, sqrt_b2;
+};
+
+__device__ __forceinline__ float bias_c1(const AdamConst& c, float s) {  // lr / (1 - b1^s)
+  return c.lr / (-expm1f(s * c.ln_b1));
+}
+__device__ __forceinline__ float bias_c2(const AdamConst& c, float s) {  // 1 / sqrt(1 - b2^s)
+  return 1.f / sqrtf(-expm1f(s * c.ln_b2));
+}
+
+// Brings one element from "state after step `last`" to "state after step last+gap" under zero
+// gradient.  c1s / c2s hold the bias terms of steps last+1 .. last+min(gap, kMaxReplay).
+__device__ __forceinline__ void replay_zero_steps(float& p, float& m, float& v, int gap,
+                                                  const float* c1s, const float* c2s,
+                                                  const AdamConst& c) {
+  if (gap <= 0) return;
+  const int n = min(gap, kMaxReplay);
+  const float m0 = m, v0 = v;
+  float mm = m0, r = sqrtf(v0);
+  if (m0 != 0.f) {
+    for (int j = 0; j < n; ++j) {
+      mm *= c.b1;
+      r *= c.sqrt_b2;
+      p -= c1s[j] * __fdividef(mm, fmaf(r, c2s[j], c.eps));
+    }
+  }
+  m = m0 * expf((float)gap * c.ln_b1);
+  v = v0 * expf((float)gap * c.ln_b2);
+}
+
+__device__ __forceinline__ void adam_real_step(float& p, float& m, float& v, float g, float c1t,
+                                               float c2t, const AdamConst& c) {
+  m = fmaf(1.f - c.b1, g - m, m);
+  v = fmaf(c.b2, v, (1.f - c.b2) * g * g);
+  p -= c1t * (m / fmaf(sqrtf(v), c2t, c.eps));
+}
+
+// One warp updates one table row of `dim` floats.  g == nullptr => replay only (flush).
+template <int V>
+__device__ __forceinline__ void adam_row(float* __restrict__ P, float* __restrict__ M,
+                                         float* __restrict__ Vv, float* __restrict__ G, int dim,
+                                         int gap, const float* c1s, const float* c2s, float c1t,
+                                         float c2t, const AdamConst& c, int lane) {
+  if (V == 4) {
+    for (int e = lane * 4; e < dim; e += 128) {
+      float4 p4 = *reinterpret_cast<float4*>(P + e);
+      float4 m4 = *reinterpret_cast<float4*>(M + e);
+      float4 v4 = *reinterpret_cast<float4*>(Vv + e);
+      float4 g4 = make_float4(0, 0, 0, 0);
+      if (G) g4 = *reinterpret_cast<float4*>(G + e);
+      float* pp = &p4.x; float* mp = &m4.x; float* vp = &v4.x; float* gp = &g4.x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        replay_zero_steps(pp[q], mp[q], vp[q], gap, c1s, c2s, c);
+        if (G) adam_real_step(pp[q], mp[q], vp[q], gp[q], c1t, c2t, c);
+      }
+      *reinterpret_cast<float4*>(P + e) = p4;
+      *reinterpret_cast<float4*>(M + e) = m4;
+      *reinterpret_cast<float4*>(Vv + e) = v4;
+      if (G) *reinterpret_cast<float4*>(G + e) = make_float4(0, 0, 0, 0);
+    }
+  } else {
+    for (int e = lane; e < dim; e += 32) {
+      float p = P[e], m = M[e], v = Vv[e];
+      replay_zero_steps(p, m, v, gap, c1s, c2s, c);
+      if (G) {
+        adam_real_step(p, m, v, G[e], c1t, c2t, c);
+        G[e] = 0.f;
+      }
+      P[e] = p; M[e] = m; Vv[e] = v;
+    }
+  }
+}
+
+struct RowsParams {
+  // side 0 = users, side 1 = items
+  float *p_gmf[2], *m_gmf[2], *v_gmf[2], *g_gmf[2];
+  float *p_mlp[2], *m_mlp[2], *v_mlp[2], *g_mlp[2];
+  int32_t* last[2];
+  int32_t* flag[2];
+  const int64_t* list[2];
+  const int32_t* tcount;
+  int64_t rows[2];
+  const int64_t* step;
+  int f, d, has_gmf, has_mlp;
+  AdamConst c;
+};
+
+// mode 0: Adam on touched rows; mode 1: flush (all rows, replay only)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q) {
+  __shared__ float c1_sm[kWarps][kMaxReplay];
+  __shared__ float c2_sm[kWarps][kMaxReplay];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* c1s = c1_sm[warp];
+  float* c2s = c2_sm[warp];
+  const int64_t step_now = *q.step;
+  const int64_t t = (MODE == 0) ? step_now + 1 : step_now;  // state is brought to "after step t"
+  const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
+  const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
+  int64_t n0, n1;
+  if (MODE == 0) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
+  const int64_t total = n0 + n1;
+  const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  for (int64_t e = wid; e < total; e += nw) {
+    const int side = e < n0 ? 0 : 1;
+    const int64_t r = (MODE == 0) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+    const int32_t last = q.last[side][r];
+    int gap;
+    if (MODE == 0) {
+      gap = (last > 0) ? (int)(t - 1 - last) : 0;
+    } else {
+      if (last <= 0 || last >= t) continue;
+      gap = (int)(t - last);
+    }
+    __syncwarp();
+    const int n = min(gap, kMaxReplay);
+    for (int j = lane; j < n; j += 32) {
+      const float s = (float)(last + 1 + j);
+      c1s[j] = bias_c1(q.c, s);
+      c2s[j] = bias_c2(q.c, s);
+    }
+    __syncwarp();
+    if (q.has_gmf) {
+      const int64_t o = r * q.f;
+      float* G = (MODE == 0) ? q.g_gmf[side] + o : nullptr;
+      if (vec) adam_row<4>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
+      else adam_row<1>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
+    }
+    if (q.has_mlp) {
+      const int64_t o = r * q.d;
+      float* G = (MODE == 0) ? q.g_mlp[side] + o : nullptr;
+      if (vec) adam_row<4>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
+      else adam_row<1>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
+    }
+    if (lane == 0) {
+      q.last[side][r] = (int32_t)t;
+      if (MODE == 0) q.flag[side][r] = 0;
+    }
+  }
+}
+
+struct DenseSeg {
+  float* p;
+  int64_t off, n;
+};
+struct DenseParams {
+  DenseSeg seg[2 * NCF_MAX_LAYERS + 2];
+  int nseg;
+  float *g, *m, *v;
+  const int64_t* step;
+  AdamConst c;
+};
+
+__global__ void adam_dense_kernel(const DenseParams q) {
+  const DenseSeg s = q.seg[blockIdx.y];
+  const int64_t t = *q.step + 1;
+  const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < s.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float p = s.p[i], m = q.m[s.off + i], v = q.v[s.off + i];
+    const float g = q.g[s.off + i];
+    adam_real_step(p, m, v, g, c1t, c2t, q.c);
+    s.p[i] = p;
+    q.m[s.off + i] = m;
+    q.v[s.off + i] = v;
+    q.g[s.off + i] = 0.f;
+  }
+}
+
+__global__ void sgd_dense_kernel(const DenseParams q, float lr) {
+  const DenseSeg s = q.seg[blockIdx.y];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < s.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    s.p[i] -= lr * q.g[s.off + i];
+    q.g[s.off + i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sgd_rows_kernel(const RowsParams q, float lr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n0 = q.tcount[0], total = n0 + q.tcount[1];
+  const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  for (int64_t e = wid; e < total; e += nw) {
+    const int side = e < n0 ? 0 : 1;
+    const int64_t r = q.list[side][side ? e - n0 : e];
+    if (q.has_gmf) {
+      float* P = q.p_gmf[side] + r * q.f;
+      float* G = q.g_gmf[side] + r * q.f;
+      for (int c = lane; c < q.f; c += 32) { P[c] -= lr * G[c]; G[c] = 0.f; }
+    }
+    if (q.has_mlp) {
+      float* P = q.p_mlp[side] + r * q.d;
+      float* G = q.g_mlp[side] + r * q.d;
+      for (int c = lane; c < q.d; c += 32) { P[c] -= lr * G[c]; G[c] = 0.f; }
+    }
+    if (lane == 0) q.flag[side][r] = 0;
+  }
+}
+
+__global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
+  if (step) *step += 1;
+  tcount[0] = 0;
+  tcount[1] = 0;
+}
+
+AdamConst make_const(NcfAdamHyper h) {
+  AdamConst c;
+  c.lr = h.lr; c.b1 = h.beta1; c.b2 = h.beta2; c.eps = h.eps;
+  c.ln_b1 = (float)log((double)h.beta1);
+  c.ln_b2 = (float)log((double)h.beta2);
+  c.sqrt_b2 = (float)sqrt((double)h.beta2);
+  return c;
+}
+
+void fill_rows(RowsParams& q, const NcfModel* m, const NcfGrads* g, const NcfAdamState* s) {
+  q.p_gmf[0] = m->embed_user_gmf; q.p_gmf[1] = m->embed_item_gmf;
+  q.p_mlp[0] = m->embed_user_mlp; q.p_mlp[1] = m->embed_item_mlp;
+  if (g) {
+    q.g_gmf[0] = g->g_user_gmf; q.g_gmf[1] = g->g_item_gmf;
+    q.g_mlp[0] = g->g_user_mlp; q.g_mlp[1] = g->g_item_mlp;
+    q.flag[0] = g->user_flag; q.flag[1] = g->item_flag;
+    q.list[0] = g->user_list; q.list[1] = g->item_list;
+    q.tcount = g->touched_count;
+  }
+  if (s) {
+    q.m_gmf[0] = s->m_user_gmf; q.m_gmf[1] = s->m_item_gmf;
+    q.v_gmf[0] = s->v_user_gmf; q.v_gmf[1] = s->v_item_gmf;
+    q.m_mlp[0] = s->m_user_mlp; q.m_mlp[1] = s->m_item_mlp;
+    q.v_mlp[0] = s->v_user_mlp; q.v_mlp[1] = s->v_item_mlp;
+    q.last[0] = s->user_last_step; q.last[1] = s->item_last_step;
+    q.step = s->step;
+  }
+  q.rows[0] = m->user_num; q.rows[1] = m->item_num;
+  q.f = m->factor_num; q.d = m->mlp_dim;
+  q.has_gmf = m->model_type != NCF_MLP;
+  q.has_mlp = m->model_type != NCF_GMF;
+}
+
+void fill_dense(DenseParams& q, const NcfModel* m) {
+  ncf::TowerShape ts = ncf::make_tower_shape(m->model_type, m->factor_num, m->num_layers);
+  int n = 0;
+  if (m->model_type != NCF_GMF) {
+    for (int k = 0; k < ts.L; ++k) {
+      q.seg[n++] = {m->mlp_w[k], ts.w_off[k], (int64_t)ts.width[k] * ts.width[k + 1]};
+      q.seg[n++] = {m->mlp_b[k], ts.b_off[k], (int64_t)ts.width[k + 1]};
+    }
+  }
+  q.seg[n++] = {m->predict_w, ts.pw_off, (int64_t)ts.predict_size};
+  q.seg[n++] = {m->predict_b, ts.pb_off, 1};
+  q.nseg = n;
+}
+
+int check_state(const NcfModel* m, const NcfAdamState* s) {
+  NCF_REQUIRE(s && s->step && s->user_last_step && s->item_last_step && s->m_tower && s->v_tower,
+              "incomplete NcfAdamState");
+  if (m->model_type != NCF_MLP)
+    NCF_REQUIRE(s->m_user_gmf && s->v_user_gmf && s->m_item_gmf && s->v_item_gmf,
+                "NcfAdamState: GMF moments are NULL");
+  if (m->model_type != NCF_GMF)
+    NCF_REQUIRE(s->m_user_mlp && s->v_user_mlp && s->m_item_mlp && s->v_item_mlp,
+                "NcfAdamState: MLP moments are NULL");
+  return NCF_OK;
+}
+
+int check_grads(const NcfModel* m, const NcfGrads* g) {
+  NCF_REQUIRE(g && g->g_tower && g->user_flag && g->item_flag && g->user_list && g->item_list &&
+                  g->touched_count,
+              "incomplete NcfGrads");
+  if (m->model_type != NCF_MLP) NCF_REQUIRE(g->g_user_gmf && g->g_item_gmf, "GMF grads are NULL");
+  if (m->model_type != NCF_GMF) NCF_REQUIRE(g->g_user_mlp && g->g_item_mlp, "MLP grads are NULL");
+  return NCF_OK;
+}
+
+}  // namespace
+
+extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
+                             NcfAdamHyper h, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  if ((rc = check_state(m, s)) != NCF_OK) return rc;
+  NCF_REQUIRE(h.beta1 > 0.f && h.beta1 < 1.f && h.beta2 > 0.f && h.beta2 < 1.f && h.eps > 0.f,
+              "ncf_adam_step: bad hyper-parameters");
+  cudaStream_t st = (cudaStream_t)stream;
+  RowsParams q{};
+  fill_rows(q, m, g, s);
+  q.c = make_const(h);
+  adam_rows_kernel<0><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+  NCF_LAUNCH_CHECK("adam_rows_kernel");
+  DenseParams dq{};
+  fill_dense(dq, m);
+  dq.g = g->g_tower; dq.m = s->m_tower; dq.v = s->v_tower; dq.step = s->step; dq.c = q.c;
+  adam_dense_kernel<<<dim3(32, dq.nseg), 256, 0, st>>>(dq);
+  NCF_LAUNCH_CHECK("adam_dense_kernel");
+  finalize_step_kernel<<<1, 1, 0, st>>>(s->step, g->touched_count);
+  NCF_LAUNCH_CHECK("finalize_step_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_adam_flush(const NcfModel* m, const NcfAdamState* s, NcfAdamHyper h,
+                              void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_state(m, s)) != NCF_OK) return rc;
+  RowsParams q{};
+  fill_rows(q, m, nullptr, s);
+  q.c = make_const(h);
+  adam_rows_kernel<1><<<ncf::num_sms() * 8, kThreads, 0, (cudaStream_t)stream>>>(q);
+  NCF_LAUNCH_CHECK("adam_rows_kernel<flush>");
+  return NCF_OK;
+}
+
+extern "C" int ncf_sgd_step(const NcfModel* m, const NcfGrads* g, float lr, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  RowsParams q{};
+  fill_rows(q, m, g, nullptr);
+  sgd_rows_kernel<<<ncf::num_sms() * 8, kThreads, 0, st>>>(q, lr);
+  NCF_LAUNCH_CHECK("sgd_rows_kernel");
+  DenseParams dq{};
+  fill_dense(dq, m);
+  dq.g = g->g_tower;
+  sgd_dense_kernel<<<dim3(32, dq.nseg), 256, 0, st>>>(dq, lr);
+  NCF_LAUNCH_CHECK("sgd_dense_kernel");
+  finalize_step_kernel<<<1, 1, 0, st>>>(nullptr, g->touched_count);
+  NCF_LAUNCH_CHECK("finalize_step_kernel");
+  return NCF_OK;
+}

@@ -1,0 +1,284 @@
+"""Tensor-level wrappers of the C ABI (one Python function per entry point of include/ncf_b200.h).
+
+All tensors must be CUDA, contiguous, and of the dtype the header states; nothing here computes on
+the host and nothing falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import NcfAdamHyper, NcfAdamState, NcfGrads, NcfModel, check, current_stream, ptr
+
+
+def tower_widths(factor_num: int, num_layers: int):
+    """[f*2^L, f*2^(L-1), ..., f] — reference src/ncf/models.py:20-26."""
+    return [factor_num << (num_layers - k) for k in range(num_layers + 1)]
+
+
+def tower_param_count(model_type: int, factor_num: int, num_layers: int) -> int:
+    return int(_lib.load().ncf_tower_param_count(model_type, factor_num, num_layers))
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        raise _lib.NcfError(f"{name} must be int64, got {t.dtype}")
+    return t
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise _lib.NcfError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def model_struct(model_type: int, factor_num: int, num_layers: int, user_num: int, item_num: int,
+                 tables, linears, predict) -> NcfModel:
+    """tables = (user_gmf, item_gmf, user_mlp, item_mlp); linears = [(w, b)]*L; predict = (w, b)."""
+    m = NcfModel()
+    m.model_type, m.factor_num, m.num_layers = model_type, factor_num, num_layers
+    m.mlp_dim = factor_num << (num_layers - 1)
+    m.user_num, m.item_num = user_num, item_num
+    m.embed_user_gmf, m.embed_item_gmf, m.embed_user_mlp, m.embed_item_mlp = (
+        ptr(_f32(t, "table")) for t in tables)
+    for k, (w, b) in enumerate(linears):
+        m.mlp_w[k] = ptr(_f32(w, "mlp weight"))
+        m.mlp_b[k] = ptr(_f32(b, "mlp bias"))
+    m.predict_w, m.predict_b = ptr(_f32(predict[0], "predict")), ptr(_f32(predict[1], "predict"))
+    return m
+
+
+# ---- a1 -----------------------------------------------------------------------------------------
+def csr_build(pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int):
+    """Sorted-column CSR of the observed pairs: (rowptr int64[U+1], col int32[P])."""
+    lib = _lib.load()
+    P = pos_user.numel()
+    dev = pos_user.device
+    rowptr = torch.empty(user_num + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    ws_bytes = lib.ncf_csr_workspace_bytes(P, user_num)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.ncf_csr_build(ptr(_i64(pos_user, "pos_user")), ptr(_i64(pos_item, "pos_item")), P,
+                            user_num, ptr(rowptr), ptr(col), ptr(ws), ws_bytes, current_stream()),
+          "ncf_csr_build")
+    return rowptr, col[:P]
+
+
+# ---- a2 -----------------------------------------------------------------------------------------
+def sample_neg(rowptr, col, pos_user, num_ng: int, item_num: int, seed: int, epoch: int,
+               p_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    P = pos_user.numel()
+    if out is None:
+        out = torch.empty(P * num_ng, dtype=torch.int64, device=pos_user.device)
+    elif out.numel() < P * num_ng:
+        raise _lib.NcfError("sample_neg: out too small")
+    colp = col if col.numel() else torch.zeros(1, dtype=torch.int32, device=pos_user.device)
+    check(lib.ncf_sample_neg(ptr(_i64(rowptr, "rowptr")), ptr(colp), ptr(_i64(pos_user, "pos_user")),
+                             P, p_offset, num_ng, item_num, seed, epoch, ptr(_i64(out, "out")),
+                             current_stream()), "ncf_sample_neg")
+    return out
+
+
+# ---- a3 -----------------------------------------------------------------------------------------
+def shuffle_epoch(pos_user, pos_item, neg_item, num_ng: int, seed: int, epoch: int, q_begin: int,
+                  count: int, out_user, out_item, out_label) -> None:
+    lib = _lib.load()
+    if min(out_user.numel(), out_item.numel(), out_label.numel()) < count:
+        raise _lib.NcfError("shuffle_epoch: output buffers too small")
+    check(lib.ncf_shuffle_epoch(ptr(_i64(pos_user, "pos_user")), ptr(_i64(pos_item, "pos_item")),
+                                ptr(neg_item) if neg_item is not None else None, pos_user.numel(),
+                                num_ng, seed, epoch, q_begin, count, ptr(_i64(out_user, "out_user")),
+                                ptr(_i64(out_item, "out_item")), ptr(_f32(out_label, "out_label")),
+                                current_stream()), "ncf_shuffle_epoch")
+
+
+# ---- a6 -----------------------------------------------------------------------------------------
+def forward(m: NcfModel, user: torch.Tensor, item: torch.Tensor,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    B = user.numel()
+    if item.numel() != B:
+        raise _lib.NcfError("forward: user and item differ in length")
+    if out is None:
+        out = torch.empty(B, dtype=torch.float32, device=user.device)
+    check(lib.ncf_forward(C.byref(m), ptr(_i64(user, "user")), ptr(_i64(item, "item")), B,
+                          ptr(_f32(out, "logits")), None, 0, current_stream()), "ncf_forward")
+    return out
+
+
+# ---- a7 / a8 --------------------------------------------------------------------------------------
+def loss_grad(logits, label, teacher_logits, alpha: float, loss_accum: torch.Tensor,
+              dlogit: Optional[torch.Tensor]) -> None:
+    lib = _lib.load()
+    if loss_accum.dtype != torch.float64:
+        raise _lib.NcfError("loss_accum must be float64")
+    check(lib.ncf_loss_grad(ptr(_f32(logits, "logits")), ptr(_f32(label, "label")),
+                            ptr(teacher_logits) if teacher_logits is not None else None, alpha,
+                            logits.numel(), ptr(loss_accum),
+                            ptr(dlogit) if dlogit is not None else None, current_stream()),
+          "ncf_loss_grad")
+
+
+# ---- gradient / optimiser state ---------------------------------------------------------------------
+@dataclass
+class GradBuffers:
+    """Owner of the tensors behind an NcfGrads struct."""
+    g_user_gmf: Optional[torch.Tensor]
+    g_item_gmf: Optional[torch.Tensor]
+    g_user_mlp: Optional[torch.Tensor]
+    g_item_mlp: Optional[torch.Tensor]
+    g_tower: torch.Tensor
+    user_flag: torch.Tensor
+    item_flag: torch.Tensor
+    user_list: torch.Tensor
+    item_list: torch.Tensor
+    touched_count: torch.Tensor
+
+    @staticmethod
+    def allocate(model_type, factor_num, num_layers, user_num, item_num, capacity, device):
+        f, d = factor_num, factor_num << (num_layers - 1)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
+        gmf, mlp = model_type != _lib.NCF_MLP, model_type != _lib.NCF_GMF
+        return GradBuffers(
+            z(user_num, f) if gmf else None, z(item_num, f) if gmf else None,
+            z(user_num, d) if mlp else None, z(item_num, d) if mlp else None,
+            z(tower_param_count(model_type, factor_num, num_layers)),
+            z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
+            z(min(capacity, user_num), dt=torch.int64), z(min(capacity, item_num), dt=torch.int64),
+            z(2, dt=torch.int32))
+
+    def struct(self) -> NcfGrads:
+        g = NcfGrads()
+        for name in ("g_user_gmf", "g_item_gmf", "g_user_mlp", "g_item_mlp", "g_tower", "user_flag",
+                     "item_flag", "user_list", "item_list", "touched_count"):
+            t = getattr(self, name)
+            setattr(g, name, ptr(t) if t is not None else None)
+        return g
+
+
+@dataclass
+class AdamBuffers:
+    """Owner of the tensors behind an NcfAdamState struct."""
+    m_user_gmf: Optional[torch.Tensor]
+    v_user_gmf: Optional[torch.Tensor]
+    m_item_gmf: Optional[torch.Tensor]
+    v_item_gmf: Optional[torch.Tensor]
+    m_user_mlp: Optional[torch.Tensor]
+    v_user_mlp: Optional[torch.Tensor]
+    m_item_mlp: Optional[torch.Tensor]
+    v_item_mlp: Optional[torch.Tensor]
+    m_tower: torch.Tensor
+    v_tower: torch.Tensor
+    user_last_step: torch.Tensor
+    item_last_step: torch.Tensor
+    step: torch.Tensor
+
+    @staticmethod
+    def allocate(model_type, factor_num, num_layers, user_num, item_num, device):
+        f, d = factor_num, factor_num << (num_layers - 1)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
+        gmf, mlp = model_type != _lib.NCF_MLP, model_type != _lib.NCF_GMF
+        nt = tower_param_count(model_type, factor_num, num_layers)
+        return AdamBuffers(
+            z(user_num, f) if gmf else None, z(user_num, f) if gmf else None,
+            z(item_num, f) if gmf else None, z(item_num, f) if gmf else None,
+            z(user_num, d) if mlp else None, z(user_num, d) if mlp else None,
+            z(item_num, d) if mlp else None, z(item_num, d) if mlp else None,
+            z(nt), z(nt), z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
+            z(1, dt=torch.int64))
+
+    def struct(self) -> NcfAdamState:
+        s = NcfAdamState()
+        for name, _ in NcfAdamState._fields_:
+            t = getattr(self, name)
+            setattr(s, name, ptr(t) if t is not None else None)
+        return s
+
+
+def train_workspace_bytes(m: NcfModel, B: int) -> int:
+    n = int(_lib.load().ncf_train_workspace_bytes(C.byref(m), B))
+    if n < 0:
+        raise _lib.NcfError("ncf_train_workspace_bytes: bad model or batch")
+    return n
+
+
+# ---- a6 + a7 + a8 + a9 ---------------------------------------------------------------------------------
+def train_step_grads(m: NcfModel, g: NcfGrads, user, item, label, teacher_logits, alpha: float,
+                     loss_accum: torch.Tensor, workspace: torch.Tensor,
+                     logits_out: Optional[torch.Tensor] = None) -> None:
+    lib = _lib.load()
+    B = user.numel()
+    if item.numel() != B or label.numel() != B:
+        raise _lib.NcfError("train_step_grads: user/item/label differ in length")
+    if loss_accum.dtype != torch.float64:
+        raise _lib.NcfError("loss_accum must be float64")
+    check(lib.ncf_train_step_grads(
+        C.byref(m), C.byref(g), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+        ptr(_f32(label, "label")), ptr(teacher_logits) if teacher_logits is not None else None,
+        alpha, B, ptr(loss_accum), ptr(logits_out) if logits_out is not None else None,
+        ptr(workspace), workspace.numel() * workspace.element_size(), current_stream()),
+        "ncf_train_step_grads")
+
+
+def backward(m: NcfModel, g: NcfGrads, user, item, dlogit, workspace: torch.Tensor) -> None:
+    """Backward from a caller-supplied dloss/dlogit (autograd compatibility path)."""
+    check(_lib.load().ncf_backward(
+        C.byref(m), C.byref(g), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+        ptr(_f32(dlogit, "dlogit")), user.numel(), ptr(workspace),
+        workspace.numel() * workspace.element_size(), current_stream()), "ncf_backward")
+
+
+# ---- a10 ------------------------------------------------------------------------------------------------
+def adam_step(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().ncf_adam_step(C.byref(m), C.byref(g), C.byref(s),
+                                    NcfAdamHyper(lr, beta1, beta2, eps), current_stream()),
+          "ncf_adam_step")
+
+
+def adam_flush(m: NcfModel, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().ncf_adam_flush(C.byref(m), C.byref(s), NcfAdamHyper(lr, beta1, beta2, eps),
+                                     current_stream()), "ncf_adam_flush")
+
+
+def sgd_step(m: NcfModel, g: NcfGrads, lr: float):
+    check(_lib.load().ncf_sgd_step(C.byref(m), C.byref(g), lr, current_stream()), "ncf_sgd_step")
+
+
+# ---- a11 ------------------------------------------------------------------------------------------------
+def eval_rank(scores: torch.Tensor, k: int):
+    """scores [n, C] -> (hit uint8[n], rank int32[n], ndcg f32[n], topk_idx int32[n, k])."""
+    lib = _lib.load()
+    if scores.dim() != 2:
+        raise _lib.NcfError("eval_rank: scores must be [n, C]")
+    n, Cc = scores.shape
+    dev = scores.device
+    hit = torch.empty(n, dtype=torch.uint8, device=dev)
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    ndcg = torch.empty(n, dtype=torch.float32, device=dev)
+    topk = torch.empty(n, k, dtype=torch.int32, device=dev)
+    check(lib.ncf_eval_rank(ptr(_f32(scores, "scores")), n, Cc, k, ptr(hit), ptr(rank), ptr(ndcg),
+                            ptr(topk), current_stream()), "ncf_eval_rank")
+    return hit, rank, ndcg, topk
+
+
+def eval_users(m: NcfModel, users: torch.Tensor, cands: torch.Tensor, k: int):
+    """users [n], cands [n, C] (column 0 = held-out item) -> (hit, rank, ndcg, topk_idx, scores)."""
+    lib = _lib.load()
+    if cands.dim() != 2 or cands.shape[0] != users.numel():
+        raise _lib.NcfError("eval_users: cands must be [n, C] with one row per user (ragged input is rejected)")
+    n, Cc = cands.shape
+    dev = users.device
+    hit = torch.empty(n, dtype=torch.uint8, device=dev)
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    ndcg = torch.empty(n, dtype=torch.float32, device=dev)
+    topk = torch.empty(n, k, dtype=torch.int32, device=dev)
+    scores = torch.empty(n, Cc, dtype=torch.float32, device=dev)
+    check(lib.ncf_eval_users(C.byref(m), ptr(_i64(users, "users")), ptr(_i64(cands, "cands")), n, Cc,
+                             k, ptr(hit), ptr(rank), ptr(ndcg), ptr(topk), ptr(scores), None, 0,
+                             current_stream()), "ncf_eval_users")
+    return hit, rank, ndcg, topk, scores

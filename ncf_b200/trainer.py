@@ -1,0 +1,204 @@
+"""The fused training step and the on-device epoch stream (sampler + shuffle + batching).
+
+`FusedTrainStep` is what the four entry points (scripts/train_neumf.py, pretrain.py,
+train_teacher.py, train_student.py) run instead of the reference inner loop
+    optimizer.zero_grad(); prediction = model(user, item); loss = criterion(prediction, label)
+    loss.backward(); optimizer.step(); total_loss += loss.item()
+(reference scripts/train_neumf.py:106-118): per step it launches
+    [teacher forward]  ->  fused forward+loss+backward  ->  sparse-row Adam / SGD
+with no host synchronisation; the loss is accumulated on the device and read once per epoch.
+`capture()` records a window of steps into a CUDA graph for the launch-bound small configs.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from .models import NCF
+
+
+class FusedTrainStep:
+    def __init__(self, model: NCF, optimizer: str = "adam", lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, max_batch: int = 256, teacher: Optional[NCF] = None,
+                 alpha: float = 0.5):
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise _lib.NcfError("FusedTrainStep needs the model on a CUDA device (no CPU path)")
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' or 'sgd'")
+        if model.dropout and model.dropout > 0:
+            raise NotImplementedError("the fused step implements dropout=0.0 (reference default)")
+        self.model, self.teacher = model, teacher
+        self.optimizer, self.lr, self.betas, self.eps, self.alpha = optimizer, float(lr), betas, eps, float(alpha)
+        self.max_batch = int(max_batch)
+        dev = p0.device
+        self.device = dev
+        mt = model.abi_type()
+        self.grads = ops.GradBuffers.allocate(mt, model.factor_num, model.num_layers, model.user_num,
+                                              model.item_num, self.max_batch, dev)
+        self.state = (ops.AdamBuffers.allocate(mt, model.factor_num, model.num_layers, model.user_num,
+                                               model.item_num, dev) if optimizer == "adam" else None)
+        self.loss_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.num_steps = 0
+        self._refresh()
+        self.workspace = torch.empty(ops.train_workspace_bytes(self._m, self.max_batch),
+                                     dtype=torch.uint8, device=dev)
+        self.teacher_logits = (torch.empty(self.max_batch, dtype=torch.float32, device=dev)
+                               if teacher is not None else None)
+        if teacher is not None:
+            teacher.eval()
+            for p in teacher.parameters():  # reference src/distillation/base.py:16-18
+                p.requires_grad = False
+        self._dirty = False  # True while some rows lag behind the dense-Adam state
+
+    def _refresh(self):
+        """Re-reads the parameter pointers (they change if the module is moved or reloaded)."""
+        self._m = self.model.abi_struct()
+        self._g = self.grads.struct()
+        self._s = self.state.struct() if self.state is not None else None
+        self._tm = self.teacher.abi_struct() if self.teacher is not None else None
+
+    # -- one optimisation step on a device batch ------------------------------------------------
+    def step(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor,
+             logits_out: Optional[torch.Tensor] = None) -> None:
+        B = user.numel()
+        if B > self.max_batch:
+            raise _lib.NcfError(f"batch {B} exceeds max_batch {self.max_batch}")
+        t_logits = None
+        if self.teacher is not None:
+            t_logits = self.teacher_logits[:B]
+            ops.forward(self._tm, user, item, out=t_logits)
+        ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
+                             self.loss_accum, self.workspace, logits_out)
+        if self.optimizer == "adam":
+            ops.adam_step(self._m, self._g, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
+            self._dirty = True
+        else:
+            ops.sgd_step(self._m, self._g, self.lr)
+        self.num_steps += 1
+
+    def flush(self) -> None:
+        """Brings every embedding row to the dense-Adam state of the current step.  Must run
+        before the weights are read (evaluation, checkpoint, state_dict)."""
+        if self.optimizer == "adam" and self._dirty:
+            ops.adam_flush(self._m, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
+            self._dirty = False
+
+    def pop_loss(self) -> float:
+        """Sum of the per-batch mean losses since the last call (one device->host read)."""
+        v = float(self.loss_accum.item())
+        self.loss_accum.zero_()
+        return v
+
+    # -- CUDA-graph window ----------------------------------------------------------------------
+    def capture(self, users: torch.Tensor, items: torch.Tensor, labels: torch.Tensor,
+                batch: int) -> "StepGraph":
+        """Captures `len(users) // batch` consecutive steps over static window buffers."""
+        return StepGraph(self, users, items, labels, batch)
+
+
+class StepGraph:
+    """A CUDA graph of consecutive FusedTrainStep.step() calls over fixed window buffers
+    (refilled in place by ncf_shuffle_epoch between replays)."""
+
+    def __init__(self, ts: FusedTrainStep, users, items, labels, batch: int):
+        n = users.numel() // batch
+        if n < 1:
+            raise _lib.NcfError("window smaller than one batch")
+        self.ts, self.n_steps, self.batch = ts, n, batch
+        self.graph = torch.cuda.CUDAGraph()
+        # Snapshot and restore the optimiser/parameter state around the warm-up and capture
+        # launches so that capturing does not advance training.
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            self.graph.capture_begin()
+            for i in range(n):
+                sl = slice(i * batch, (i + 1) * batch)
+                ts.step(users[sl], items[sl], labels[sl])
+            self.graph.capture_end()
+        torch.cuda.current_stream().wait_stream(stream)
+        ts.num_steps -= n  # capture records, it does not execute
+
+    def replay(self) -> None:
+        self.graph.replay()
+        self.ts.num_steps += self.n_steps
+        if self.ts.optimizer == "adam":
+            self.ts._dirty = True
+
+
+class EpochStream:
+    """On-device replacement of `NCFData.ng_sample()` + `DataLoader(shuffle=True)` (reference
+    src/data/datasets.py:53-83, scripts/train_neumf.py:55,102): a CSR of the observed pairs, a
+    Philox negative sampler, and a keyed permutation that lays the epoch's S = P*(1+num_ng)
+    samples out in shuffled order, window by window."""
+
+    def __init__(self, pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int, item_num: int,
+                 num_ng: int, seed: int = 0, p_offset: int = 0):
+        self.pos_user = pos_user.to(torch.int64).contiguous()
+        self.pos_item = pos_item.to(torch.int64).contiguous()
+        self.user_num, self.item_num, self.num_ng, self.seed = int(user_num), int(item_num), int(num_ng), int(seed)
+        self.p_offset = int(p_offset)
+        self.P = self.pos_user.numel()
+        self.S = self.P * (1 + self.num_ng)
+        self.rowptr, self.col = ops.csr_build(self.pos_user, self.pos_item, self.user_num)
+        self.neg_item = torch.empty(self.P * self.num_ng, dtype=torch.int64, device=self.pos_user.device)
+        self.epoch = -1
+
+    def begin_epoch(self, epoch: int) -> None:
+        """ng_sample(): draws this epoch's negatives."""
+        self.epoch = int(epoch)
+        ops.sample_neg(self.rowptr, self.col, self.pos_user, self.num_ng, self.item_num, self.seed,
+                       self.epoch, self.p_offset, out=self.neg_item)
+
+    def fill(self, q_begin: int, count: int, out_user, out_item, out_label) -> None:
+        """Writes stream positions [q_begin, q_begin+count) of the current epoch."""
+        ops.shuffle_epoch(self.pos_user, self.pos_item, self.neg_item, self.num_ng, self.seed,
+                          self.epoch, q_begin, count, out_user, out_item, out_label)
+
+    def num_batches(self, batch: int) -> int:
+        return (self.S + batch - 1) // batch  # drop_last=False like the reference DataLoader
+
+
+def train_epoch(ts: FusedTrainStep, stream: EpochStream, epoch: int, batch: int,
+                window_steps: int = 64, use_graph: bool = True, cache: Optional[dict] = None):
+    """One epoch of the reference loop (scripts/train_neumf.py:98-120) on the fused path.
+    Returns (avg_loss, num_batches)."""
+    dev = ts.device
+    stream.begin_epoch(epoch)
+    S, nb = stream.S, stream.num_batches(batch)
+    cache = cache if cache is not None else {}
+    W = max(1, min(window_steps, S // batch)) if S >= batch else 1
+    key = ("win", batch, W)
+    if key not in cache:
+        cache[key] = (torch.empty(W * batch, dtype=torch.int64, device=dev),
+                      torch.empty(W * batch, dtype=torch.int64, device=dev),
+                      torch.empty(W * batch, dtype=torch.float32, device=dev))
+    wu, wi, wl = cache[key]
+    graph = None
+    q = 0
+    full_windows = (S // batch) // W if S >= batch else 0
+    for _ in range(full_windows):
+        stream.fill(q, W * batch, wu, wi, wl)
+        if use_graph:
+            gkey = ("graph", batch, W)
+            if gkey not in cache:
+                cache[gkey] = ts.capture(wu, wi, wl, batch)
+            graph = cache[gkey]
+            graph.replay()
+        else:
+            for i in range(W):
+                sl = slice(i * batch, (i + 1) * batch)
+                ts.step(wu[sl], wi[sl], wl[sl])
+        q += W * batch
+    # tail: remaining full batches, then the short last batch
+    while q < S:
+        cnt = min(batch, S - q)
+        stream.fill(q, cnt, wu, wi, wl)
+        ts.step(wu[:cnt], wi[:cnt], wl[:cnt])
+        q += cnt
+    total = ts.pop_loss()
+    return total / nb, nb
