@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""Benchmark of the NCF training hot path (BASELINE.json metric: NeuMF train samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload at N=1: BASELINE.json configs[3] — NeuMF (factor 32, 3 tower layers: 256->128->64->32)
+on the synthetic MovieLens-20M shape (138 493 users x 26 744 items, ~20M interactions, 4
+negatives per positive), batch 65 536, Adam lr 1e-3.  It is the config the metric "train
+samples/s @1/2/4/8 B200" is quoted on and it fits one GPU; configs[1] (ML-1M shape, batch 256) is
+launch-latency-bound and is a parity-test case (`--workload ml1m` runs it).
+A "step" is one optimisation step on one batch: [catch-up of lagging rows] -> fused
+gather+forward+loss+backward -> sparse-row Adam.  Under torchrun (N>1) every rank runs the same
+per-GPU batch on its own replica (weak scaling).
+
+The JSON line carries `value` (device-resident inputs), `e2e` (host buffers through the public
+API with H2D/D2H inside the timed region), `roofline` of the dominant kernel, `cpu_baseline`
+(the reference's CPU op sequence, oracle/torch_port.py, timed on this box's host cores) and the
+clocks seen during the timed region.  `--impl reference` times only that CPU port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (synthetic shape, factor_num, num_layers, batch)
+    "ml20m": ("ml20m", 32, 3, 65536),
+    "ml1m": ("ml1m", 8, 3, 256),
+}
+METRIC, UNIT = "NeuMF train samples/s", "samples/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, budget_s=None):
+    """Times the reference's CPU op sequence (oracle/torch_port.py) on this box's host cores on
+    the same config: one step = one batch of the workload's size through forward, BCE, autograd
+    backward (dense embedding grads) and dense Adam.  Returns (samples/s, ms/step, steps, cores)."""
+    import torch
+    from ncf_b200.synth import SHAPES
+    from oracle import torch_port as tp
+    shape, f, L, B = WORKLOADS[workload]
+    U, I, _, _ = SHAPES[shape]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = tp.init_params(U, I, f, L, "NeuMF-end", seed=0)
+    tr = tp.CpuTrainer(P, "NeuMF-end", lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    n_distinct = 4
+    batches = [(torch.randint(0, U, (B,), generator=g), torch.randint(0, I, (B,), generator=g),
+                (torch.rand(B, generator=g) < 0.2).float()) for _ in range(n_distinct)]
+    for w in range(warmup):
+        tr.step(*batches[w % n_distinct])
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(steps):
+        tr.step(*batches[k % n_distinct])
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * B / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape, f, L, B = WORKLOADS[args.workload]
+    sps, ms, done, cores = cpu_reference_run(args.workload, args.steps, max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.workload, 1),
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} steps of batch {B} (uniform random indices of the workload's table "
+                                   f"shape), reference op sequence on torch CPU with dense Adam"},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(workload, n_gpus):
+    shape, f, L, B = WORKLOADS[workload]
+    from ncf_b200.synth import SHAPES
+    U, I, total, _ = SHAPES[shape]
+    return {"workload": f"NeuMF f={f} L={L} (tower {f << L}->{f}) on synthetic {shape} shape "
+                        f"({U} users x {I} items, ~{total} interactions, 4 neg/pos), batch {B} per GPU, Adam lr 1e-3",
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus}",
+            "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
+                  "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ncf_b200 import ops
+    from ncf_b200.models import NCF
+    from ncf_b200.synth import make_interactions
+    from ncf_b200.trainer import EpochStream, FusedTrainStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ncf_b200 hot path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shape, f, L, B = WORKLOADS[args.workload]
+    K, W = args.steps, max(3, args.warmup)
+
+    inter = make_interactions(shape, device=dev)
+    U, I = inter.user_num, inter.item_num
+    torch.manual_seed(0)
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
+    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    # every rank draws from its own slice of the epoch stream (weak scaling: B per GPU per step)
+    stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=20250605)
+    stream.begin_epoch(0)
+    n_batches = W + K
+    need = n_batches * B
+    q0 = rank * need
+    if q0 + need > stream.S:
+        raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
+    bu = torch.empty(need, dtype=torch.int64, device=dev)
+    bi = torch.empty(need, dtype=torch.int64, device=dev)
+    bl = torch.empty(need, dtype=torch.float32, device=dev)
+    stream.fill(q0, need, bu, bi, bl)
+    sl = lambda k: slice(k * B, (k + 1) * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sync_grads = make_dp_sync(ts, world) if world > 1 else None
+
+    def one_step(k):
+        if sync_grads is None:
+            ts.step(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+        else:
+            sync_grads(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for k in range(W):
+        one_step(k)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + K):
+        one_step(k)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * K * B / (ms_total * 1e-3)
+    launches_per_step = 7  # mark, catch-up, fused tile, tower wgrad, row Adam, tower Adam, finalize
+
+    # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
+    phases = None
+    if world == 1:
+        names = ["adam_prepare", "train_step_grads", "adam_step"]
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        torch.cuda.synchronize()
+        for k in range(K):
+            u, i, y = bu[sl(W + k)], bi[sl(W + k)], bl[sl(W + k)]
+            ev[k][0].record()
+            ops.adam_prepare(ts._m, ts._g, ts._s, u, i, ts.lr)
+            ev[k][1].record()
+            ops.train_step_grads(ts._m, ts._g, u, i, y, None, 1.0, ts.loss_accum, ts.workspace)
+            ev[k][2].record()
+            ops.adam_step(ts._m, ts._g, ts._s, ts.lr)
+            ev[k][3].record()
+        torch.cuda.synchronize()
+        phases = {n: sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(K)) / K
+                  for j, n in enumerate(names)}
+
+    # ---- end to end: host buffers, H2D + D2H inside the timed region -----------------------------------
+    hu = bu.cpu().pin_memory(); hi = bi.cpu().pin_memory(); hl = bl.cpu().pin_memory()
+    du = torch.empty(B, dtype=torch.int64, device=dev)
+    di = torch.empty(B, dtype=torch.int64, device=dev)
+    dl = torch.empty(B, dtype=torch.float32, device=dev)
+    host_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def e2e_step(k):
+        du.copy_(hu[sl(k)], non_blocking=True)
+        di.copy_(hi[sl(k)], non_blocking=True)
+        dl.copy_(hl[sl(k)], non_blocking=True)
+        if sync_grads is None:
+            ts.step(du, di, dl)
+        else:
+            sync_grads(du, di, dl)
+        host_loss.copy_(ts.loss_accum, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the reference reads loss.item() every step
+        return float(host_loss[0])
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        e2e_step(k)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * K * B / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    d = f << (L - 1)
+    R = 2 * f + 2 * d
+    roofline = None
+    if phases is not None:
+        dom = max(phases, key=phases.get)
+        # algorithmic bytes per launch (DESIGN.md "Algorithmic bytes")
+        nu = len(torch.unique(bu[sl(W)])); ni = len(torch.unique(bi[sl(W)]))
+        alg = {
+            "train_step_grads": (4 * R + 24) * B,              # row gather + indices + label
+            "adam_step": 6 * 4 * (f + d) * (nu + ni),          # p, m, v read + write on touched rows
+            "adam_prepare": 16 * B + 6 * 4 * (f + d) * (nu + ni),
+        }[dom]
+        achieved = alg / (phases[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg, "launch_ms": phases[dom],
+                    "phase_ms": phases,
+                    "step_level": {"bytes_per_sample": 4 * R * 7 + 24,
+                                   "achieved": (4 * R * 7 + 24) * value / 1e9,
+                                   "frac": (4 * R * 7 + 24) * value / 1e9 / peak}}
+
+    # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only) ---------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, done, cores = cpu_reference_run(args.workload, steps=40, warmup=1, budget_s=15.0)
+        cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{done} steps of batch {B} ({ms:.0f} ms/step) of the same config: reference op "
+                                  f"sequence on torch CPU, dense autograd embedding grads + dense Adam"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": 8,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "final_loss": float(host_loss[0]),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def make_dp_sync(ts, world):
+    """Data-parallel step over replicated tables (see ncf_b200/dist.py)."""
+    from ncf_b200.dist import ReplicatedDataParallel
+    dp = ReplicatedDataParallel(ts)
+    return dp.step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="ml20m")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

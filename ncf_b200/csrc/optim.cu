@@ -106,7 +106,9 @@ struct RowsParams {
   AdamConst c;
 };
 
-// mode 0: Adam on touched rows; mode 1: flush (all rows, replay only)
+// mode 0: Adam step on the touched rows; mode 1: flush (all rows, replay only);
+// mode 2: catch-up (touched rows, replay only) — run BEFORE the forward of a step so that the rows
+// the batch is about to read are at the dense-Adam state of the previous step.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q) {
   __shared__ float c1_sm[kWarps][kMaxReplay];
@@ -119,12 +121,12 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
   const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
   const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
   int64_t n0, n1;
-  if (MODE == 0) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
+  if (MODE != 1) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
   const int64_t total = n0 + n1;
   const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
   for (int64_t e = wid; e < total; e += nw) {
     const int side = e < n0 ? 0 : 1;
-    const int64_t r = (MODE == 0) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+    const int64_t r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
     const int32_t last = q.last[side][r];
     int gap;
     if (MODE == 0) {
@@ -215,6 +217,20 @@ __global__ void __launch_bounds__(kThreads) sgd_rows_kernel(const RowsParams q, 
       for (int c = lane; c < q.d; c += 32) { P[c] -= lr * G[c]; G[c] = 0.f; }
     }
     if (lane == 0) q.flag[side][r] = 0;
+  }
+}
+
+// Registers the distinct rows of a batch in the touched lists (same protocol as the training
+// kernel, which then finds the flags already set).
+__global__ void mark_rows_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ item,
+                                 int64_t B, int64_t U, int64_t I, int32_t* uflag, int32_t* iflag,
+                                 int64_t* ulist, int64_t* ilist, int32_t* tcount) {
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B;
+       b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = user[b], it = item[b];
+    if (u < 0 || u >= U || it < 0 || it >= I) continue;
+    if (atomicExch(&uflag[u], 1) == 0) ulist[atomicAdd(&tcount[0], 1)] = u;
+    if (atomicExch(&iflag[it], 1) == 0) ilist[atomicAdd(&tcount[1], 1)] = it;
   }
 }
 
@@ -315,6 +331,29 @@ extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdam
   NCF_LAUNCH_CHECK("adam_dense_kernel");
   finalize_step_kernel<<<1, 1, 0, st>>>(s->step, g->touched_count);
   NCF_LAUNCH_CHECK("finalize_step_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
+                                NcfAdamHyper h, const int64_t* user, const int64_t* item, int64_t B,
+                                void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  if ((rc = check_state(m, s)) != NCF_OK) return rc;
+  NCF_REQUIRE(B > 0 && user && item, "ncf_adam_prepare: empty batch or null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (B + 255) / 256;
+  if (blocks > 4 * ncf::num_sms()) blocks = 4 * ncf::num_sms();
+  mark_rows_kernel<<<(int)blocks, 256, 0, st>>>(user, item, B, m->user_num, m->item_num,
+                                               g->user_flag, g->item_flag, g->user_list,
+                                               g->item_list, g->touched_count);
+  NCF_LAUNCH_CHECK("mark_rows_kernel");
+  RowsParams q{};
+  fill_rows(q, m, g, s);
+  q.c = make_const(h);
+  adam_rows_kernel<2><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+  NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
   return NCF_OK;
 }
 

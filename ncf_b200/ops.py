@@ -234,6 +234,16 @@ def backward(m: NcfModel, g: NcfGrads, user, item, dlogit, workspace: torch.Tens
 
 
 # ---- a10 ------------------------------------------------------------------------------------------------
+def adam_prepare(m: NcfModel, g: NcfGrads, s: NcfAdamState, user, item, lr, beta1=0.9, beta2=0.999,
+                 eps=1e-8):
+    """Registers the batch's rows and replays their pending zero-gradient Adam steps; must
+    precede train_step_grads of the same batch."""
+    check(_lib.load().ncf_adam_prepare(C.byref(m), C.byref(g), C.byref(s),
+                                       NcfAdamHyper(lr, beta1, beta2, eps), ptr(_i64(user, "user")),
+                                       ptr(_i64(item, "item")), user.numel(), current_stream()),
+          "ncf_adam_prepare")
+
+
 def adam_step(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().ncf_adam_step(C.byref(m), C.byref(g), C.byref(s),
                                     NcfAdamHyper(lr, beta1, beta2, eps), current_stream()),

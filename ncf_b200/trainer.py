@@ -70,6 +70,10 @@ class FusedTrainStep:
         if self.teacher is not None:
             t_logits = self.teacher_logits[:B]
             ops.forward(self._tm, user, item, out=t_logits)
+        if self.optimizer == "adam":
+            # rows this batch reads must first catch up with the dense-Adam trajectory
+            ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
+                             self.betas[1], self.eps)
         ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
                              self.loss_accum, self.workspace, logits_out)
         if self.optimizer == "adam":
@@ -137,14 +141,17 @@ class EpochStream:
     samples out in shuffled order, window by window."""
 
     def __init__(self, pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int, item_num: int,
-                 num_ng: int, seed: int = 0, p_offset: int = 0):
+                 num_ng: int, seed: int = 0, p_offset: int = 0, observed=None):
         self.pos_user = pos_user.to(torch.int64).contiguous()
         self.pos_item = pos_item.to(torch.int64).contiguous()
         self.user_num, self.item_num, self.num_ng, self.seed = int(user_num), int(item_num), int(num_ng), int(seed)
         self.p_offset = int(p_offset)
         self.P = self.pos_user.numel()
         self.S = self.P * (1 + self.num_ng)
-        self.rowptr, self.col = ops.csr_build(self.pos_user, self.pos_item, self.user_num)
+        # pairs to reject against (train_mat of the reference); defaults to the positives themselves
+        ou, oi = observed if observed is not None else (self.pos_user, self.pos_item)
+        self.rowptr, self.col = ops.csr_build(ou.to(torch.int64).contiguous(),
+                                              oi.to(torch.int64).contiguous(), self.user_num)
         self.neg_item = torch.empty(self.P * self.num_ng, dtype=torch.int64, device=self.pos_user.device)
         self.epoch = -1
 
@@ -181,9 +188,10 @@ def train_epoch(ts: FusedTrainStep, stream: EpochStream, epoch: int, batch: int,
     graph = None
     q = 0
     full_windows = (S // batch) // W if S >= batch else 0
-    for _ in range(full_windows):
+    for w in range(full_windows):
         stream.fill(q, W * batch, wu, wi, wl)
-        if use_graph:
+        # the very first window runs eagerly: it loads the kernels before any capture
+        if use_graph and (w > 0 or ("graph", batch, W) in cache):
             gkey = ("graph", batch, W)
             if gkey not in cache:
                 cache[gkey] = ts.capture(wu, wi, wl, batch)

@@ -1,0 +1,375 @@
+"""GPU parity: the CUDA path, called through the C ABI (ncf_b200.ops -> ctypes -> libncf_b200.so),
+against (a) the committed reference goldens and (b) the CPU oracle on seeded inputs.
+
+Bar (north star): sampled indices, gathered rows and eval rankings bit-exact; logits, losses,
+gradients and updated weights within 1e-5 relative in fp32 (tests/util.py states how "relative"
+is measured and why a handful of Adam elements get a wider bound).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncf_numpy as onp
+from oracle import philox as oph
+from tests.util import assert_close, assert_close_adam, group, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_CASES = ["train_gmf_f8", "train_mlp_f8_l3", "train_neumf_f8_l3", "train_neumf_f32_l2",
+               "train_neumf_f6_l2", "train_neumf_f5_l1", "train_neumf_f64_l3", "train_neumf_f8_l3_sgd"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def build_model(params, meta, model_type=None, f=None, L=None):
+    from ncf_b200.models import NCF
+    mt = model_type or meta["model_type"]
+    f = f or meta["f"]
+    L = L or meta["L"]
+    m = NCF(meta["U"], meta["I"], f, L, 0.0, mt)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    return m.to(dev())
+
+
+def state_np(model):
+    return {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+
+
+def _batch(z, meta, t):
+    n = meta["B"] - meta["short_last"] if (meta.get("short_last") and t == meta["T"] - 1) else meta["B"]
+    return tuple(torch.from_numpy(z[k][t, :n]).to(dev()) for k in ("user", "item", "label"))
+
+
+USED = {"GMF": ("embed_user_GMF", "embed_item_GMF", "predict_layer"),
+        "MLP": ("embed_user_MLP", "embed_item_MLP", "MLP_layers", "predict_layer")}
+
+
+def used_keys(model_type, keys):
+    if model_type in USED:
+        return [k for k in keys if k.startswith(USED[model_type])]
+    return list(keys)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_forward_matches_reference(name):
+    z, meta = load_golden(name)
+    model = build_model(group(z, "init"), meta).eval()
+    u, i, _ = _batch(z, meta, 0)
+    with torch.no_grad():
+        logits = model(u, i)
+    assert_close(logits.cpu().numpy(), z["logits0"], "logits")
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_fused_step_gradients_match_reference(name):
+    """Gradients left in the NcfGrads buffers by ncf_train_step_grads == autograd's."""
+    from ncf_b200 import ops
+    z, meta = load_golden(name)
+    model = build_model(group(z, "init"), meta)
+    u, i, y = _batch(z, meta, 0)
+    B = u.numel()
+    mt = model.abi_type()
+    g = ops.GradBuffers.allocate(mt, meta["f"], meta["L"], meta["U"], meta["I"], B, dev())
+    m = model.abi_struct()
+    ws = torch.empty(ops.train_workspace_bytes(m, B), dtype=torch.uint8, device=dev())
+    loss = torch.zeros(1, dtype=torch.float64, device=dev())
+    logits = torch.empty(B, device=dev())
+    ops.train_step_grads(m, g.struct(), u, i, y, None, 1.0, loss, ws, logits)
+    assert_close(logits.cpu().numpy(), z["logits0"], "logits")
+    assert abs(loss.item() - z["loss"][0]) <= 2e-6 * abs(z["loss"][0])
+    ref = group(z, "grad0")
+    tables = {"embed_user_GMF.weight": g.g_user_gmf, "embed_item_GMF.weight": g.g_item_gmf,
+              "embed_user_MLP.weight": g.g_user_mlp, "embed_item_MLP.weight": g.g_item_mlp}
+    for k, buf in tables.items():
+        if k in ref:
+            assert_close(buf.cpu().numpy(), ref[k], f"grad {k}")
+        else:
+            assert buf is None  # autograd leaves unused tables without a gradient
+    flat = g.g_tower.cpu().numpy()
+    off = 0
+    keys = [f"MLP_layers.{3 * k + 1}.{s}" for k in range(meta["L"]) for s in ("weight", "bias")]
+    keys += ["predict_layer.weight", "predict_layer.bias"]
+    sd = model.state_dict()
+    for k in keys:
+        n = sd[k].numel()
+        piece = flat[off:off + n].reshape(tuple(sd[k].shape))
+        off += n
+        if k in ref:
+            assert_close(piece, ref[k], f"grad {k}")
+        else:
+            assert not piece.any()
+    assert off == flat.size
+    # touched lists = distinct users / items of the batch
+    nu, ni = g.touched_count.cpu().tolist()
+    assert sorted(g.user_list[:nu].cpu().tolist()) == sorted(set(u.cpu().tolist()))
+    assert sorted(g.item_list[:ni].cpu().tolist()) == sorted(set(i.cpu().tolist()))
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_training_steps_match_reference(name):
+    """T optimiser steps through FusedTrainStep (lazy sparse-row Adam / SGD) == the reference's
+    dense optimiser; includes rows that skip steps and a short last batch."""
+    from ncf_b200.trainer import FusedTrainStep
+    z, meta = load_golden(name)
+    model = build_model(group(z, "init"), meta)
+    ts = FusedTrainStep(model, optimizer=meta["optimizer"], lr=meta["lr"], max_batch=meta["B"])
+    check = assert_close_adam if meta["optimizer"] == "adam" else assert_close
+    for t in range(meta["T"]):
+        u, i, y = _batch(z, meta, t)
+        ts.step(u, i, y)
+        got = ts.pop_loss()
+        assert abs(got - z["loss"][t]) <= 5e-6 * abs(z["loss"][t]), f"loss at step {t}"
+        if t == 0:
+            ts.flush()
+            for k, ref in group(z, "after1").items():
+                check(state_np(model)[k], ref, f"after step 1: {k}")
+    ts.flush()
+    got = state_np(model)
+    for k, ref in group(z, "final").items():
+        check(got[k], ref, f"final {k}")
+    # parameters the model type does not use never move (autograd gives them no gradient)
+    init = group(z, "init")
+    for k in set(init) - set(used_keys(meta["model_type"], init)):
+        assert np.array_equal(got[k], init[k]), k
+
+
+def test_lazy_adam_equals_dense_oracle_over_long_gaps():
+    """Rows that go untouched for many steps (beyond the exact-replay window too) still land on
+    the dense-Adam trajectory after a flush."""
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    U, I, f, L, B, T = 40, 30, 8, 2, 16, 230
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev())
+    params = {k: v.copy() for k, v in state_np(model).items()}
+    ts = FusedTrainStep(model, optimizer="adam", lr=1e-3, max_batch=B)
+    opt = onp.DenseAdam(lr=1e-3)
+    for t in range(T):
+        # users 0..3 / items 0..3 only at steps 0 and 200: a 199-step gap (> 160 replayed exactly)
+        lo = 0 if t in (0, 200) else 4
+        u = rng.integers(lo, U, B)
+        i = rng.integers(lo, I, B)
+        y = (rng.random(B) < 0.3).astype(np.float32)
+        logits = onp.forward(params, u, i, "NeuMF-end")
+        _, dl = onp.loss_and_dlogit(logits, y)
+        opt.step(params, onp.backward(params, u, i, "NeuMF-end", dl))
+        ts.step(*(torch.from_numpy(a).to(dev()) for a in (u, i, y)))
+    ts.flush()
+    got = state_np(model)
+    for k in params:
+        # 230 chained steps: the two fp32 trajectories drift apart a little; 2e-4 still separates
+        # "dense-equivalent" from "rows frozen while untouched" (which is off by ~1e-1 here)
+        assert_close_adam(got[k], params[k], k, rtol=2e-4, outlier_frac=5e-3, outlier_rtol=5e-3)
+
+
+def test_kd_response_matches_reference():
+    from ncf_b200.trainer import FusedTrainStep
+    z, meta = load_golden("kd_response")
+    tm = dict(meta, **meta["teacher"])
+    sm = dict(meta, **meta["student"])
+    teacher = build_model(group(z, "teacher"), tm)
+    student = build_model(group(z, "init"), sm)
+    ts = FusedTrainStep(student, optimizer="adam", lr=meta["lr"], max_batch=meta["B"],
+                        teacher=teacher, alpha=meta["alpha"])
+    for t in range(meta["T"]):
+        u, i, y = (torch.from_numpy(z[k][t]).to(dev()) for k in ("user", "item", "label"))
+        if t == 0:
+            with torch.no_grad():
+                assert_close(teacher(u, i).cpu().numpy(), z["teacher_logits0"], "teacher logits")
+        ts.step(u, i, y)
+        assert abs(ts.pop_loss() - z["loss"][t]) <= 5e-6 * abs(z["loss"][t])
+    ts.flush()
+    got = state_np(student)
+    for k, ref in group(z, "final").items():
+        assert_close_adam(got[k], ref, f"KD final {k}")
+    for k, ref in group(z, "teacher").items():  # the teacher is frozen (base.py:16-18)
+        assert np.array_equal(state_np(teacher)[k], ref)
+
+
+def test_pretrain_init_then_sgd_matches_reference():
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep
+    z, meta = load_golden("neumf_pre_sgd")
+    model = NCF(meta["U"], meta["I"], meta["f"], meta["L"], 0.0, "NeuMF-pre")
+    torch.manual_seed(meta["reseed"])
+    model.load_pretrain_weights({k: torch.from_numpy(v) for k, v in group(z, "gmf").items()},
+                                {k: torch.from_numpy(v) for k, v in group(z, "mlp").items()})
+    for k, ref in group(z, "init").items():  # same tables, same tower, same re-drawn predict layer
+        assert np.array_equal(model.state_dict()[k].numpy(), ref), k
+    model = model.to(dev())
+    ts = FusedTrainStep(model, optimizer="sgd", lr=meta["lr"], max_batch=meta["B"])
+    for t in range(meta["T"]):
+        u, i, y = (torch.from_numpy(z[k][t]).to(dev()) for k in ("user", "item", "label"))
+        ts.step(u, i, y)
+        assert abs(ts.pop_loss() - z["loss"][t]) <= 5e-6 * abs(z["loss"][t])
+    got = state_np(model)
+    for k, ref in group(z, "final").items():
+        assert_close(got[k], ref, f"final {k}")
+
+
+def test_autograd_compat_path_matches_reference():
+    """An unmodified reference loop (criterion + loss.backward() + torch.optim.Adam) on our module."""
+    z, meta = load_golden("train_neumf_f8_l3")
+    model = build_model(group(z, "init"), meta)
+    opt = torch.optim.Adam(model.parameters(), lr=meta["lr"])
+    crit = torch.nn.BCEWithLogitsLoss()
+    for t in range(meta["T"]):
+        u, i, y = _batch(z, meta, t)
+        opt.zero_grad()
+        loss = crit(model(u, i), y)
+        loss.backward()
+        if t == 0:
+            for k, ref in group(z, "grad0").items():
+                p = dict(model.named_parameters())[k]
+                assert_close(p.grad.cpu().numpy(), ref, f"grad {k}")
+        opt.step()
+        assert abs(loss.item() - z["loss"][t]) <= 5e-6 * abs(z["loss"][t])
+    got = state_np(model)
+    for k, ref in group(z, "final").items():
+        assert_close_adam(got[k], ref, f"final {k}")
+
+
+@pytest.mark.parametrize("name", ["metrics_neumf_f8_l3", "metrics_gmf_f8"])
+def test_eval_matches_reference(name):
+    from ncf_b200 import ops
+    from ncf_b200.metrics import evaluate
+    z, meta = load_golden(name)
+    k = meta["k"]
+    # (1) ranking kernel on the reference's own scores: HR / NDCG / top-k bit-exact
+    scores = torch.from_numpy(z["scores"]).to(dev())
+    hit, rank, ndcg, topk = ops.eval_rank(scores, k)
+    assert hit.cpu().tolist() == z["HR"].tolist()
+    nd = [0.0 if r < 0 else 1.0 / np.log2(r + 2) for r in rank.cpu().tolist()]
+    assert nd == z["NDCG"].tolist()
+    want = np.stack([onp.topk_indices(s, k) for s in z["scores"]])
+    assert np.array_equal(topk.cpu().numpy(), want)
+    assert_close(ndcg.cpu().numpy(), z["NDCG"], "ndcg (fp32 on device)", rtol=1e-6)
+    # (2) end to end: gather + tower + rank in one call
+    model = build_model(group(z, "init"), meta).eval()
+    users = torch.from_numpy(z["users"]).to(dev())
+    cands = torch.from_numpy(z["cands"]).to(dev())
+    res = evaluate(model, users, cands, k)
+    assert_close(res.scores.cpu().numpy(), z["scores"], "scores")
+    # rankings may only differ where the reference scores are closer than the fp32 tolerance
+    s = z["scores"]
+    tol = 2e-5 * np.abs(s).max()
+    for n in range(s.shape[0]):
+        srt = -np.sort(-s[n])
+        if np.min(srt[:k] - srt[1:k + 1]) > tol:
+            assert res.hit[n].item() == z["HR"][n]
+            assert res.topk[n].cpu().tolist() == want[n].tolist()
+    assert abs(res.hit.float().mean().item() - z["HR"].mean()) <= 1.0 / s.shape[0]
+
+
+def test_eval_rank_edge_cases():
+    from ncf_b200 import ops
+    # ties: the lower candidate index wins, so an all-equal row ranks the held-out item first
+    s = torch.zeros(3, 100, device=dev())
+    s[1, 5] = 1.0
+    s[2, 1:12] = 2.0
+    hit, rank, ndcg, topk = ops.eval_rank(s, 10)
+    assert rank.cpu().tolist() == [0, 1, -1]
+    assert hit.cpu().tolist() == [1, 1, 0]
+    assert topk[0].cpu().tolist() == list(range(10))
+    assert topk[1].cpu().tolist() == [5, 0, 1, 2, 3, 4, 6, 7, 8, 9]
+    # C = 1, k = 1 and a wide row (C = 1024)
+    hit, rank, _, _ = ops.eval_rank(torch.randn(4, 1, device=dev()), 1)
+    assert rank.cpu().tolist() == [0, 0, 0, 0]
+    w = torch.randn(5, 1024, device=dev())
+    _, _, _, topk = ops.eval_rank(w, 17)
+    assert np.array_equal(topk.cpu().numpy(), np.stack([onp.topk_indices(r, 17) for r in w.cpu().numpy()]))
+    # empty input and ragged / bad arguments
+    e = ops.eval_rank(torch.empty(0, 100, device=dev()), 10)
+    assert e[0].numel() == 0
+    from ncf_b200._lib import NcfError
+    with pytest.raises(NcfError):
+        ops.eval_rank(torch.zeros(2, 5, device=dev()), 6)
+
+
+def test_sampler_csr_shuffle_bit_exact():
+    from ncf_b200 import ops
+    rng = np.random.default_rng(3)
+    U, I, num_ng = 300, 120, 4
+    pairs = np.unique(np.stack([rng.integers(0, U, 6000), rng.integers(0, I, 6000)], 1), axis=0)
+    pairs = pairs[rng.permutation(pairs.shape[0])]
+    pairs = pairs[pairs[:, 0] != 7]        # a user with no interactions
+    dense = np.stack([np.full(I - 1, 9), np.arange(I - 1)], 1)  # a user who saw all but one item
+    pairs = np.concatenate([pairs[pairs[:, 0] != 9], dense])
+    pu, pi = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
+    tu, ti = torch.from_numpy(pu).to(dev()), torch.from_numpy(pi).to(dev())
+    rowptr, col = ops.csr_build(tu, ti, U)
+    o_rowptr, o_col = oph.csr_build(pu, pi, U)
+    assert np.array_equal(rowptr.cpu().numpy(), o_rowptr)
+    assert np.array_equal(col.cpu().numpy(), o_col)
+    for epoch in (0, 1, 5):
+        neg = ops.sample_neg(rowptr, col, tu, num_ng, I, seed=1234567890123, epoch=epoch)
+        want = oph.sample_neg(o_rowptr, o_col, pu, num_ng, I, 1234567890123, epoch)
+        assert np.array_equal(neg.cpu().numpy(), want)
+        observed = set(zip(pu.tolist(), pi.tolist()))
+        assert not (set(zip(np.repeat(pu, num_ng).tolist(), want.tolist())) & observed)
+    assert (want[np.repeat(pu, num_ng) == 9] == I - 1).all()  # only one legal item for user 9
+    # sharded sampling: two halves with p_offset reproduce the single-call result
+    h = pu.shape[0] // 2
+    a = ops.sample_neg(rowptr, col, tu[:h].contiguous(), num_ng, I, 1234567890123, 5)
+    b = ops.sample_neg(rowptr, col, tu[h:].contiguous(), num_ng, I, 1234567890123, 5, p_offset=h)
+    assert np.array_equal(torch.cat([a, b]).cpu().numpy(), want)
+    # epoch stream
+    S = pu.shape[0] * (1 + num_ng)
+    ou = torch.empty(S, dtype=torch.int64, device=dev())
+    oi = torch.empty(S, dtype=torch.int64, device=dev())
+    ol = torch.empty(S, dtype=torch.float32, device=dev())
+    ops.shuffle_epoch(tu, ti, neg, num_ng, 77, 5, 0, S, ou, oi, ol)
+    wu, wi, wl = oph.shuffle_epoch(pu, pi, want, num_ng, 77, 5, 0, S)
+    assert np.array_equal(ou.cpu().numpy(), wu)
+    assert np.array_equal(oi.cpu().numpy(), wi)
+    assert np.array_equal(ol.cpu().numpy(), wl)
+    # a window in the middle equals the same slice of the full stream
+    ops.shuffle_epoch(tu, ti, neg, num_ng, 77, 5, 1000, 512, ou, oi, ol)
+    assert np.array_equal(ou[:512].cpu().numpy(), wu[1000:1512])
+
+
+def test_empty_and_invalid_inputs():
+    from ncf_b200 import ops
+    from ncf_b200._lib import NcfError
+    from ncf_b200.models import NCF
+    model = NCF(10, 10, 8, 2, 0.0, "NeuMF-end").to(dev()).eval()
+    e = torch.empty(0, dtype=torch.int64, device=dev())
+    with torch.no_grad():
+        assert model(e, e).numel() == 0
+        bad = model(torch.tensor([3, 11], device=dev()), torch.tensor([2, 2], device=dev()))
+    assert torch.isfinite(bad[0]) and torch.isnan(bad[1])  # out-of-range index is loud, not silent
+    with pytest.raises(NcfError):
+        ops.forward(model.abi_struct(), torch.zeros(2, dtype=torch.int64), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(NcfError):
+        ops.forward(model.abi_struct(), torch.zeros(2, dtype=torch.int32, device=dev()),
+                    torch.zeros(2, dtype=torch.int32, device=dev()))
+
+
+def test_graph_window_equals_eager_steps():
+    """A CUDA-graph window of steps updates the model exactly like the same steps run eagerly."""
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import EpochStream, FusedTrainStep, train_epoch
+    rng = np.random.default_rng(5)
+    U, I, P, B = 200, 150, 3000, 128
+    pu = torch.from_numpy(rng.integers(0, U, P)).to(dev())
+    pi = torch.from_numpy(rng.integers(0, I, P)).to(dev())
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(1)
+        model = NCF(U, I, 8, 3, 0.0, "NeuMF-end").to(dev())
+        ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+        stream = EpochStream(pu, pi, U, I, num_ng=4, seed=42)
+        cache = {}
+        losses = [train_epoch(ts, stream, e, B, window_steps=8, use_graph=use_graph, cache=cache)[0]
+                  for e in range(2)]
+        ts.flush()
+        results.append((losses, state_np(model), ts.num_steps))
+    (l0, s0, n0), (l1, s1, n1) = results
+    assert n0 == n1 == 2 * ((P * 5 + B - 1) // B)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a)
+    for k in s0:  # atomics reorder fp32 sums run to run, hence a tolerance rather than equality
+        assert_close_adam(s1[k], s0[k], k, rtol=1e-4, outlier_frac=5e-3, outlier_rtol=5e-3)
