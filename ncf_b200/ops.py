@@ -138,19 +138,28 @@ class GradBuffers:
     user_list: torch.Tensor
     item_list: torch.Tensor
     touched_count: torch.Tensor
+    flat: Optional[torch.Tensor] = None  # all float gradients as one buffer (one all-reduce in DP)
 
     @staticmethod
     def allocate(model_type, factor_num, num_layers, user_num, item_num, capacity, device):
         f, d = factor_num, factor_num << (num_layers - 1)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
         gmf, mlp = model_type != _lib.NCF_MLP, model_type != _lib.NCF_GMF
+        shapes = [(user_num, f) if gmf else None, (item_num, f) if gmf else None,
+                  (user_num, d) if mlp else None, (item_num, d) if mlp else None,
+                  (tower_param_count(model_type, factor_num, num_layers),)]
+        sizes = [0 if s is None else (s[0] * s[1] if len(s) == 2 else s[0]) for s in shapes]
+        sizes = [(n + 3) // 4 * 4 for n in sizes]  # keep every piece 16-byte aligned
+        flat = z(sum(sizes))
+        pieces, off = [], 0
+        for s, n in zip(shapes, sizes):
+            numel = 0 if s is None else (s[0] * s[1] if len(s) == 2 else s[0])
+            pieces.append(None if s is None else flat[off:off + numel].view(*s))
+            off += n
         return GradBuffers(
-            z(user_num, f) if gmf else None, z(item_num, f) if gmf else None,
-            z(user_num, d) if mlp else None, z(item_num, d) if mlp else None,
-            z(tower_param_count(model_type, factor_num, num_layers)),
-            z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
+            *pieces, z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
             z(min(capacity, user_num), dt=torch.int64), z(min(capacity, item_num), dt=torch.int64),
-            z(2, dt=torch.int32))
+            z(2, dt=torch.int32), flat)
 
     def struct(self) -> NcfGrads:
         g = NcfGrads()
