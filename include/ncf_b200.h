@@ -41,6 +41,13 @@ extern "C" {
 #define NCF_MLP 1
 #define NCF_NEUMF 2
 
+/* tower_math: arithmetic of the tower contractions (embedding path, loss and optimiser are always
+ * fp32).  NCF_MATH_FP32 keeps fp32 accuracy (error-compensated 3xTF32 on the tensor pipe, or fp32
+ * FMA for shapes the tensor path does not cover) and is what the 1e-5 parity bar is stated for;
+ * NCF_MATH_TF32 is single-pass TF32 (10-bit mantissa inputs, fp32 accumulate), ~3x fewer MMAs. */
+#define NCF_MATH_FP32 0
+#define NCF_MATH_TF32 1
+
 /* Parameters of one NCF model (reference src/ncf/models.py:11-34).  mlp_dim = factor_num *
  * 2^(num_layers-1); tower layer k maps width factor_num*2^(num_layers-k) -> half of it. */
 typedef struct NcfModel {
@@ -48,6 +55,8 @@ typedef struct NcfModel {
   int32_t factor_num;
   int32_t num_layers;
   int32_t mlp_dim;
+  int32_t tower_math; /* NCF_MATH_* */
+  int32_t reserved;
   int64_t user_num;
   int64_t item_num;
   float* embed_user_gmf; /* [user_num, factor_num]  embed_user_GMF.weight */

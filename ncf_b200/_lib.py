@@ -19,7 +19,8 @@ _f = C.c_void_p  # device pointers travel as integers
 class NcfModel(C.Structure):
     _fields_ = [
         ("model_type", C.c_int32), ("factor_num", C.c_int32), ("num_layers", C.c_int32),
-        ("mlp_dim", C.c_int32), ("user_num", C.c_int64), ("item_num", C.c_int64),
+        ("mlp_dim", C.c_int32), ("tower_math", C.c_int32), ("reserved", C.c_int32),
+        ("user_num", C.c_int64), ("item_num", C.c_int64),
         ("embed_user_gmf", _f), ("embed_item_gmf", _f), ("embed_user_mlp", _f), ("embed_item_mlp", _f),
         ("mlp_w", _f * NCF_MAX_LAYERS), ("mlp_b", _f * NCF_MAX_LAYERS),
         ("predict_w", _f), ("predict_b", _f),

@@ -82,10 +82,17 @@ extern "C" int ncf_eval_rank(const float* scores, int64_t n, int32_t C, int32_t 
   return NCF_OK;
 }
 
+namespace ncf {
+int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t workspace_bytes,
+                     cudaStream_t st);
+}
+
+// workspace = [scores n*C floats (used only when scores_out is NULL)] [forward workspace]
 extern "C" int64_t ncf_eval_workspace_bytes(const NcfModel* m, int64_t n, int32_t C) {
-  (void)m;
   if (n < 0 || C < 1) return -1;
-  return ncf::align_up(n * C * 4, 256) + 256;
+  const int64_t fw = ncf_forward_workspace_bytes(m, n * C);
+  if (fw < 0) return -1;
+  return ncf::align_up(n * C * 4, 256) + fw + 256;
 }
 
 extern "C" int ncf_eval_users(const NcfModel* m, const int64_t* users, const int64_t* cands,
@@ -99,14 +106,13 @@ extern "C" int ncf_eval_users(const NcfModel* m, const int64_t* users, const int
   NCF_REQUIRE(k >= 1 && k <= C, "ncf_eval_users: k=%d outside [1,C=%d]", k, C);
   if (n == 0) return NCF_OK;
   NCF_REQUIRE(users && cands, "ncf_eval_users: null pointer");
-  float* scores = scores_out;
-  if (!scores) {
-    if (!workspace || workspace_bytes < ncf_eval_workspace_bytes(m, n, C)) {
-      ncf::set_error("ncf_eval_users: workspace too small");
-      return NCF_ERR_WORKSPACE;
-    }
-    scores = (float*)workspace;
+  if (!workspace || workspace_bytes < ncf_eval_workspace_bytes(m, n, C)) {
+    ncf::set_error("ncf_eval_users: workspace too small");
+    return NCF_ERR_WORKSPACE;
   }
+  float* scores = scores_out ? scores_out : (float*)workspace;
+  char* fw = (char*)workspace + ncf::align_up(n * C * 4, 256);
+  const int64_t fw_bytes = workspace_bytes - ncf::align_up(n * C * 4, 256);
   TileParams p{};
   ncf::fill_model_params(p, m);
   p.user = users;
@@ -115,7 +121,7 @@ extern "C" int ncf_eval_users(const NcfModel* m, const int64_t* users, const int
   p.B = n * C;
   p.invB = 1.f;
   p.logits = scores;
-  rc = ncf::launch_generic_forward(p, (cudaStream_t)stream);
+  rc = ncf::forward_dispatch(p, m, fw, fw_bytes, (cudaStream_t)stream);
   if (rc != NCF_OK) return rc;
   return ncf_eval_rank(scores, n, C, k, hit, rank, ndcg, topk_idx, stream);
 }

@@ -48,16 +48,35 @@ int64_t scratch_floats(const NcfModel* m, int64_t B) {
 
 }  // namespace
 
+namespace ncf {
+
+// Forward over p.B samples on whichever tile kernel the shape is eligible for.  The tensor-pipe
+// path needs mma_split_floats(p) floats of workspace for the pre-split weights.
+int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t workspace_bytes,
+                     cudaStream_t st) {
+  if (mma_tile_rows(p) == 0) return launch_generic_forward(p, st);
+  const int64_t need = mma_split_floats(p) * 4;
+  if (!workspace || workspace_bytes < need) {
+    set_error("forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    return NCF_ERR_WORKSPACE;
+  }
+  int rc = mma_prepare_weights(p, (float*)workspace, st);
+  if (rc != NCF_OK) return rc;
+  return launch_mma_forward(p, tower_passes(m), st);
+}
+
+}  // namespace ncf
+
 extern "C" int64_t ncf_forward_workspace_bytes(const NcfModel* m, int64_t B) {
-  (void)m;
   (void)B;
-  return 0;
+  if (ncf::validate_model(m) != NCF_OK) return -1;
+  TileParams p{};
+  ncf::fill_model_params(p, m);
+  return ncf::mma_tile_rows(p) ? ncf::align_up(ncf::mma_split_floats(p) * 4, 256) : 0;
 }
 
 extern "C" int ncf_forward(const NcfModel* m, const int64_t* user, const int64_t* item, int64_t B,
                            float* logits, void* workspace, int64_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   int rc = ncf::validate_model(m);
   if (rc != NCF_OK) return rc;
   NCF_REQUIRE(B >= 0, "ncf_forward: negative batch");
@@ -70,7 +89,7 @@ extern "C" int ncf_forward(const NcfModel* m, const int64_t* user, const int64_t
   p.B = B;
   p.invB = 1.f / (float)B;
   p.logits = logits;
-  return ncf::launch_generic_forward(p, (cudaStream_t)stream);
+  return ncf::forward_dispatch(p, m, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int ncf_loss_grad(const float* logits, const float* label, const float* teacher_logits,
@@ -88,7 +107,10 @@ extern "C" int ncf_loss_grad(const float* logits, const float* label, const floa
 
 extern "C" int64_t ncf_train_workspace_bytes(const NcfModel* m, int64_t B) {
   if (ncf::validate_model(m) != NCF_OK || B < 0) return -1;
-  return ncf::align_up(scratch_floats(m, B) * 4, 256) + 256;
+  TileParams p{};
+  ncf::fill_model_params(p, m);
+  const int64_t floats = ncf::mma_tile_rows(p) ? ncf::mma_split_floats(p) : scratch_floats(m, B);
+  return ncf::align_up(floats * 4, 256) + 256;
 }
 
 static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* user,
@@ -148,6 +170,11 @@ static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* use
   p.invB = 1.f / (float)B;
   p.logits = logits_out;
   p.loss_accum = loss_accum;
+  if (ncf::mma_tile_rows(p) != 0) {
+    rc = ncf::mma_prepare_weights(p, (float*)workspace, (cudaStream_t)stream);
+    if (rc != NCF_OK) return rc;
+    return ncf::launch_mma_train(p, ncf::tower_passes(m), (cudaStream_t)stream);
+  }
   if (m->model_type != NCF_GMF) {
     float* ws = (float*)workspace;
     for (int k = 1; k < p.L; ++k) { p.act[k] = ws; ws += B * p.W[k]; }

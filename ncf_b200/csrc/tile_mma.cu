@@ -1,0 +1,600 @@
+// Tensor-pipe version of the fused forward / forward+loss+backward tile kernel for towers whose
+// widths are multiples of 8 (factor_num % 8 == 0).  Same data flow as tile_generic.cu — one CTA
+// owns a tile of TM samples whose activations stay in shared memory for the whole
+// forward+backward — but every contraction runs on warp-level mma.sync.m16n8k8 TF32 tiles:
+//
+//   PASSES == 3 ("fp32"): error-compensated 3xTF32.  Each fp32 operand x is split into
+//       hi = tf32(x), lo = tf32(x - hi) and  x*w ~= lo*hi' + hi*lo' + hi*hi'  accumulated in fp32,
+//       which keeps logits / gradients within the 1e-5 parity bar of the fp32 reference;
+//   PASSES == 1 ("tf32"): plain TF32 (10-bit mantissa), 3x fewer MMAs, stated looser tolerance.
+//
+// Three GEMM flavours per layer k (tile = TM samples):
+//   forward   H_{k+1}[m][n] = relu(sum_c H_k[m][c] W_k[n][c] + b_k[n])       A: smem act, B: W_k
+//   backward  d_k[m][c]     = (sum_n d_{k+1}[m][n] W_k[n][c]) * [H_k > 0]     A: smem act, B: W_k^T
+//   wgrad     dW_k[n][c]   += sum_m d_{k+1}[m][n] H_k[m][c]                   A, B: smem act
+// Weights are pre-split (hi, lo) once per step by split_weights_kernel into the exact fragment
+// order the B operand is consumed in, and streamed from L2 through a double-buffered cp.async
+// stage; activations are split in registers when their fragments are loaded.  wgrad results and
+// embedding-row gradients leave the CTA as vector REDs (dW_k is small and L2-resident).
+//
+// Replaces reference src/ncf/models.py:97-118 and scripts/train_neumf.py:112-114.
+#include "common.cuh"
+#include "tile_params.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kStageRow = 48;          // floats per staged weight row: 2 k-steps x 16 + 16 pad
+constexpr int kStageRows = 128;        // output rows per staged block
+constexpr int kStageFloats = kStageRows * kStageRow;
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+struct Split {
+  uint32_t hi, lo;
+};
+template <int PASSES>
+__device__ __forceinline__ Split split_tf32(float x) {
+  Split s;
+  s.hi = f2tf32(x);
+  s.lo = 0;
+  if (PASSES == 3) s.lo = f2tf32(x - __uint_as_float(s.hi));
+  return s;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// ---- pre-split weights ---------------------------------------------------------------------------
+// For a GEMM with `rows` output rows and contraction length `len` (multiple of 8), element
+// (r, c) lands at  [c/8][r][ ((c%8)/2)*4 + (c%2) ]  (hi)  and  +2 (lo): one 16-float record per
+// (k-step, row) holding the four (k, k+1) pairs as [hi0, hi1, lo0, lo1].
+__global__ void split_weights_kernel(const TileParams p) {
+  const int k = blockIdx.y;
+  if (k >= p.L) return;
+  const int K = p.W[k], N = p.W[k + 1];
+  const float* W = p.w[k];
+  float* wf = p.wsplit_f[k];
+  float* wb = p.wsplit_b[k];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * K; idx += gridDim.x * blockDim.x) {
+    const int n = idx / K, c = idx % K;
+    const float x = W[idx];
+    const float hi = __uint_as_float(f2tf32(x));
+    const float lo = __uint_as_float(f2tf32(x - hi));
+    {  // forward operand: rows = n, contraction = c
+      float* d = wf + ((int64_t)(c >> 3) * N + n) * 16 + ((c & 7) >> 1) * 4 + (c & 1);
+      d[0] = hi;
+      d[2] = lo;
+    }
+    {  // backward operand: rows = c, contraction = n
+      float* d = wb + ((int64_t)(n >> 3) * K + c) * 16 + ((n & 7) >> 1) * 4 + (n & 1);
+      d[0] = hi;
+      d[2] = lo;
+    }
+  }
+}
+
+// ---- flavour 1: A = activations in smem [TM][len] (stride lda), B = streamed pre-split weights -----
+// Output block: TM x nb (nb <= 128, multiple of 8) starting at output row `row0` of the weight
+// operand.  Warp (wm, wn) owns rows [wm*16*MT, +16*MT) x cols [wn*8*NT, +8*NT).
+// epi(m, col, v0, v1) receives the pairs (col, col+1) of row m.
+template <int PASSES, int MT, int NT, typename Epi>
+__device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int lda, int len,
+                                                const float* __restrict__ wsplit, int rows_total,
+                                                int row0, int nb, int WN, int tm_rows, float* stage,
+                                                Epi epi) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp / WN, wn = warp % WN;
+  const bool active = wm * 16 * MT < tm_rows;  // surplus warps only help with staging and syncs
+  const int nks = len >> 3;                 // k-steps
+  const int nchunks = (nks + 1) >> 1;       // 2 k-steps per staged chunk
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+  auto load_chunk = [&](int c, float* buf) {
+    const int ks0 = c * 2, n_ks = min(2, nks - ks0);
+    const int total = n_ks * nb * 4;  // 16-byte pieces
+    for (int idx = tid; idx < total; idx += kThreads) {
+      const int quad = idx & 3, r = (idx >> 2) % nb, ks = (idx >> 2) / nb;
+      cp_async16(buf + r * kStageRow + ks * 16 + quad * 4,
+                 wsplit + ((int64_t)(ks0 + ks) * rows_total + row0 + r) * 16 + quad * 4);
+    }
+    cp_async_commit();
+  };
+
+  load_chunk(0, stage);
+  for (int c = 0; c < nchunks; ++c) {
+    float* buf = stage + (c & 1) * kStageFloats;
+    if (c + 1 < nchunks) {
+      load_chunk(c + 1, stage + ((c + 1) & 1) * kStageFloats);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int n_ks = active ? min(2, nks - c * 2) : 0;
+    for (int ks = 0; ks < n_ks; ++ks) {
+      const int k0 = (c * 2 + ks) * 8;
+      uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const float* ap = A + (wm * 16 * MT + i * 16 + g) * lda + k0 + 2 * t;
+        const float2 x0 = *reinterpret_cast<const float2*>(ap);
+        const float2 x1 = *reinterpret_cast<const float2*>(ap + 8 * lda);
+        const Split s0 = split_tf32<PASSES>(x0.x), s2 = split_tf32<PASSES>(x0.y);
+        const Split s1 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
+        ahi[i][0] = s0.hi; ahi[i][1] = s1.hi; ahi[i][2] = s2.hi; ahi[i][3] = s3.hi;
+        alo[i][0] = s0.lo; alo[i][1] = s1.lo; alo[i][2] = s2.lo; alo[i][3] = s3.lo;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(buf + (wn * 8 * NT + j * 8 + g) * kStageRow +
+                                                          ks * 16 + t * 4);
+        const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
+        const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          if (PASSES == 3) {
+            mma_tf32(acc[i][j], alo[i], bh0, bh1);
+            mma_tf32(acc[i][j], ahi[i], bl0, bl1);
+          }
+          mma_tf32(acc[i][j], ahi[i], bh0, bh1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int m = wm * 16 * MT + i * 16 + g;
+      const int col = row0 + wn * 8 * NT + j * 8 + 2 * t;
+      epi(m, col, acc[i][j][0], acc[i][j][1]);
+      epi(m + 8, col, acc[i][j][2], acc[i][j][3]);
+    }
+}
+
+// Dispatch on the (MT, NT) tiling for a TM x nb output block.
+template <int PASSES, int TM, typename Epi>
+__device__ __forceinline__ void gemm_act_weight_block(const float* A, int lda, int len,
+                                                      const float* wsplit, int rows_total, int row0,
+                                                      int nb, float* stage, Epi epi) {
+  // warps along n: up to 4 (8 when TM == 32 and nb allows); the rest along m
+  constexpr int MTILES = TM / 16;
+  if (TM == 64) {
+    if (nb == 128) gemm_act_weight<PASSES, 2, 4>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 64) gemm_act_weight<PASSES, 2, 2>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 32) gemm_act_weight<PASSES, 2, 1>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 16) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 2, TM, stage, epi);
+    else gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 1, TM, stage, epi);
+  } else {
+    static_assert(MTILES == 2 || MTILES == 4, "TM must be 32 or 64");
+    if (nb == 128) gemm_act_weight<PASSES, 1, 4>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 64) gemm_act_weight<PASSES, 1, 2>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 32) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    else if (nb == 16) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 2, TM, stage, epi);
+    else gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 1, TM, stage, epi);
+  }
+}
+
+// ---- flavour 2: dW[n][c] += sum_m D[m][n] * H[m][c], both operands are smem activations ---------------
+// Output tiles of (16*MT) x (8*NT) are dealt round-robin to the warps; NT is even.  Results leave
+// as 16-byte REDs: thanks to the column interleave a thread owns 4 consecutive c per (row, tile pair).
+template <int PASSES, int TM, int MT, int NT>
+__device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd, int N,
+                                           const float* __restrict__ H, int ldh, int K,
+                                           float* __restrict__ gw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles_n = (N + 16 * MT - 1) / (16 * MT), tiles_c = K / (8 * NT);
+  for (int tile = warp; tile < tiles_n * tiles_c; tile += kWarps) {
+    const int n0 = (tile / tiles_c) * 16 * MT, c0 = (tile % tiles_c) * 8 * NT;
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    for (int m0 = 0; m0 < TM; m0 += 8) {
+      uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int n = n0 + i * 16 + 2 * g;  // MMA rows g, g+8 <-> n, n+1
+        float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
+        if (n < N) {
+          x0 = *reinterpret_cast<const float2*>(D + (m0 + t) * ldd + n);
+          x1 = *reinterpret_cast<const float2*>(D + (m0 + t + 4) * ldd + n);
+        }
+        const Split s0 = split_tf32<PASSES>(x0.x), s1 = split_tf32<PASSES>(x0.y);
+        const Split s2 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
+        ahi[i][0] = s0.hi; ahi[i][1] = s1.hi; ahi[i][2] = s2.hi; ahi[i][3] = s3.hi;
+        alo[i][0] = s0.lo; alo[i][1] = s1.lo; alo[i][2] = s2.lo; alo[i][3] = s3.lo;
+      }
+#pragma unroll
+      for (int jj = 0; jj < NT / 2; ++jj) {
+        const int c = c0 + jj * 16 + 2 * g;  // tile 2jj col g <-> c, tile 2jj+1 col g <-> c+1
+        const float2 y0 = *reinterpret_cast<const float2*>(H + (m0 + t) * ldh + c);
+        const float2 y1 = *reinterpret_cast<const float2*>(H + (m0 + t + 4) * ldh + c);
+        const Split e0 = split_tf32<PASSES>(y0.x), o0 = split_tf32<PASSES>(y0.y);
+        const Split e1 = split_tf32<PASSES>(y1.x), o1 = split_tf32<PASSES>(y1.y);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          if (PASSES == 3) {
+            mma_tf32(acc[i][2 * jj], alo[i], e0.hi, e1.hi);
+            mma_tf32(acc[i][2 * jj], ahi[i], e0.lo, e1.lo);
+            mma_tf32(acc[i][2 * jj + 1], alo[i], o0.hi, o1.hi);
+            mma_tf32(acc[i][2 * jj + 1], ahi[i], o0.lo, o1.lo);
+          }
+          mma_tf32(acc[i][2 * jj], ahi[i], e0.hi, e1.hi);
+          mma_tf32(acc[i][2 * jj + 1], ahi[i], o0.hi, o1.hi);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const int n = n0 + i * 16 + 2 * g;
+#pragma unroll
+      for (int jj = 0; jj < NT / 2; ++jj) {
+        const int c = c0 + jj * 16 + 4 * t;
+        const float* e = acc[i][2 * jj];
+        const float* o = acc[i][2 * jj + 1];
+        if (n < N) red_add4(gw + (int64_t)n * K + c, make_float4(e[0], o[0], e[1], o[1]));
+        if (n + 1 < N) red_add4(gw + (int64_t)(n + 1) * K + c, make_float4(e[2], o[2], e[3], o[3]));
+      }
+    }
+  }
+}
+
+template <int PASSES, int TM>
+__device__ __forceinline__ void wgrad_dispatch(const float* D, int ldd, int N, const float* H, int ldh,
+                                               int K, float* gw) {
+  if ((N & 31) == 0 && (K & 31) == 0) gemm_wgrad<PASSES, TM, 2, 4>(D, ldd, N, H, ldh, K, gw);
+  else gemm_wgrad<PASSES, TM, 1, 2>(D, ldd, N, H, ldh, K, gw);
+}
+
+// ---- the tile kernel --------------------------------------------------------------------------------
+template <int PASSES, int TM, bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TileParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int MI = TM / kWarps;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool has_gmf = p.type != NCF_MLP, has_mlp = p.type != NCF_GMF;
+  const int f = p.f, d = p.d, L = p.L;
+
+  float* gu_s = smem + p.gmf_off;
+  float* gi_s = gu_s + TM * f;
+  float* stage = smem + p.stage_off;
+  float* dl_s = smem + p.misc_off;
+  float* ls_s = dl_s + TM;
+  int64_t* u_s = reinterpret_cast<int64_t*>(ls_s + TM);
+  int64_t* i_s = u_s + TM;
+  auto act = [&](int k) { return smem + p.smem_off[k]; };
+  auto lda = [&](int k) { return p.W[k] + 8; };
+
+  const int64_t ntiles = (p.B + TM - 1) / TM;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TM;
+    __syncthreads();
+    if (tid < TM) {
+      const int64_t b = base + tid;
+      int64_t u = -1, it = -1;
+      if (b < p.B) {
+        u = p.user[p.user_div > 0 ? b / p.user_div : b];
+        it = p.item[b];
+        if (u < 0 || u >= p.U || it < 0 || it >= p.I) { u = -2; it = -2; }
+      }
+      u_s[tid] = u;
+      i_s[tid] = it;
+    }
+    __syncthreads();
+
+    // ---- gather (one warp per sample row; 16-byte coalesced loads) -------------------------------
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int m = warp + kWarps * i;
+      const int64_t u = u_s[m], it = i_s[m];
+      const bool ok = u >= 0;
+      if (has_mlp) {
+        float* x = act(0) + m * lda(0);
+        const float* ru = p.eum + (ok ? u : 0) * d;
+        const float* ri = p.eim + (ok ? it : 0) * d;
+        for (int c = lane * 4; c < d; c += 128) {
+          const float4 a = ok ? ldg4(ru + c) : make_float4(0, 0, 0, 0);
+          const float4 b4 = ok ? ldg4(ri + c) : make_float4(0, 0, 0, 0);
+          *reinterpret_cast<float4*>(x + c) = a;
+          *reinterpret_cast<float4*>(x + d + c) = b4;
+        }
+      }
+      if (has_gmf) {
+        const float* ru = p.eug + (ok ? u : 0) * f;
+        const float* ri = p.eig + (ok ? it : 0) * f;
+        for (int c = lane; c < f; c += 32) {
+          gu_s[m * f + c] = ok ? __ldg(ru + c) : 0.f;
+          gi_s[m * f + c] = ok ? __ldg(ri + c) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- tower forward ------------------------------------------------------------------------------
+    if (has_mlp) {
+      for (int k = 0; k < L; ++k) {
+        const int K = p.W[k], N = p.W[k + 1];
+        float* out = act(k + 1);
+        const int ldo = lda(k + 1);
+        const float* bias = p.b[k];
+        for (int n0 = 0; n0 < N; n0 += kStageRows) {
+          const int nb = min(kStageRows, N - n0);
+          gemm_act_weight_block<PASSES, TM>(act(k), lda(k), K, p.wsplit_f[k], N, n0, nb, stage,
+                                            [&](int m, int col, float v0, float v1) {
+                                              const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + col));
+                                              *reinterpret_cast<float2*>(out + m * ldo + col) =
+                                                  make_float2(fmaxf(v0 + bb.x, 0.f), fmaxf(v1 + bb.y, 0.f));
+                                            });
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- predict layer + loss -------------------------------------------------------------------------
+    const float* hL = act(L);
+    const int ldL = lda(L);
+    const int fl = p.W[L];
+    const int mlp_w_off = (p.type == NCF_NEUMF) ? f : 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int m = warp + kWarps * i;
+      const int64_t b = base + m;
+      float s = 0.f;
+      if (has_gmf)
+        for (int c = lane; c < f; c += 32) s = fmaf(__ldg(&p.pw[c]), gu_s[m * f + c] * gi_s[m * f + c], s);
+      if (has_mlp)
+        for (int c = lane; c < fl; c += 32) s = fmaf(__ldg(&p.pw[mlp_w_off + c]), hL[m * ldL + c], s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        float x = s + __ldg(p.pb);
+        const bool ok = (b < p.B) && u_s[m] >= 0;
+        if (b < p.B && u_s[m] == -2) x = __int_as_float(0x7fc00000);
+        if (b < p.B && p.logits != nullptr) p.logits[b] = x;
+        if (TRAIN) {
+          float dl = 0.f, ls = 0.f;
+          if (ok && p.dlogit_in != nullptr) {
+            dl = p.dlogit_in[b];
+          } else if (ok) {
+            const float y = p.label[b];
+            const float e = expf(-fabsf(x));
+            const float bce = fmaxf(x, 0.f) - x * y + log1pf(e);
+            const float sig = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+            if (p.teacher != nullptr) {
+              const float df = x - p.teacher[b];
+              ls = p.alpha * bce + (1.f - p.alpha) * df * df;
+              dl = (p.alpha * (sig - y) + (1.f - p.alpha) * 2.f * df) * p.invB;
+            } else {
+              ls = bce;
+              dl = (sig - y) * p.invB;
+            }
+          }
+          dl_s[m] = dl;
+          ls_s[m] = ls;
+        }
+      }
+    }
+    if (!TRAIN) continue;
+    __syncthreads();
+
+    // ---- loss, predict-layer gradients, touched lists ------------------------------------------------------
+    if (warp == 0) {
+      float ls = 0.f, dsum = 0.f;
+      for (int m = lane; m < TM; m += 32) { ls += ls_s[m]; dsum += dl_s[m]; }
+      ls = warp_sum(ls);
+      dsum = warp_sum(dsum);
+      if (lane == 0) {
+        if (p.loss_accum != nullptr) atomicAdd(p.loss_accum, (double)ls * (double)p.invB);
+        atomicAdd(&p.gt[p.pb_off], dsum);
+      }
+    }
+    for (int c = tid; c < p.predict_size; c += kThreads) {
+      float s = 0.f;
+      if (has_gmf && c < f) {
+        for (int m = 0; m < TM; ++m) s = fmaf(dl_s[m], gu_s[m * f + c] * gi_s[m * f + c], s);
+      } else {
+        const int j = c - mlp_w_off;
+        for (int m = 0; m < TM; ++m) s = fmaf(dl_s[m], hL[m * ldL + j], s);
+      }
+      atomicAdd(&p.gt[p.pw_off + c], s);
+    }
+    if (tid < TM && u_s[tid] >= 0) {
+      const int64_t u = u_s[tid], it = i_s[tid];
+      if (atomicExch(&p.uflag[u], 1) == 0) p.ulist[atomicAdd(&p.tcount[0], 1)] = u;
+      if (atomicExch(&p.iflag[it], 1) == 0) p.ilist[atomicAdd(&p.tcount[1], 1)] = it;
+    }
+    __syncthreads();
+
+    // ---- GMF branch backward ---------------------------------------------------------------------------------
+    if (has_gmf) {
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int m = warp + kWarps * i;
+        const int64_t u = u_s[m], it = i_s[m];
+        if (u < 0) continue;
+        const float dl = dl_s[m];
+        for (int c = lane; c < f; c += 32) {
+          const float w = __ldg(&p.pw[c]) * dl;
+          atomicAdd(&p.gug[u * f + c], w * gi_s[m * f + c]);
+          atomicAdd(&p.gig[it * f + c], w * gu_s[m * f + c]);
+        }
+      }
+    }
+
+    // ---- tower backward ----------------------------------------------------------------------------------------
+    if (has_mlp) {
+      {  // delta_L = dl * predict_w_mlp * relu'(h_L), in place
+        float* dL = act(L);
+        for (int idx = tid; idx < TM * fl; idx += kThreads) {
+          const int m = idx / fl, c = idx % fl;
+          const float h = dL[m * ldL + c];
+          dL[m * ldL + c] = (h > 0.f) ? dl_s[m] * __ldg(&p.pw[mlp_w_off + c]) : 0.f;
+        }
+      }
+      __syncthreads();
+      for (int k = L - 1; k >= 0; --k) {
+        const int K = p.W[k], N = p.W[k + 1];
+        const float* dn = act(k + 1);  // delta_{k+1} [TM][N]
+        const int ldd = lda(k + 1);
+        // bias gradient: column sums of delta_{k+1}
+        for (int n = tid; n < N; n += kThreads) {
+          float s = 0.f;
+          for (int m = 0; m < TM; ++m) s += dn[m * ldd + n];
+          atomicAdd(&p.gt[p.b_off[k] + n], s);
+        }
+        // weight gradient
+        wgrad_dispatch<PASSES, TM>(dn, ldd, N, act(k), lda(k), K, p.gt + p.w_off[k]);
+        __syncthreads();  // every read of H_k is done before it is overwritten by delta_k
+        float* hk = act(k);
+        const int ldh = lda(k);
+        for (int c0 = 0; c0 < K; c0 += kStageRows) {
+          const int nb = min(kStageRows, K - c0);
+          if (k > 0) {
+            gemm_act_weight_block<PASSES, TM>(dn, ldd, N, p.wsplit_b[k], K, c0, nb, stage,
+                                              [&](int m, int col, float v0, float v1) {
+                                                float2* q = reinterpret_cast<float2*>(hk + m * ldh + col);
+                                                const float2 h = *q;
+                                                *q = make_float2(h.x > 0.f ? v0 : 0.f, h.y > 0.f ? v1 : 0.f);
+                                              });
+          } else {
+            gemm_act_weight_block<PASSES, TM>(dn, ldd, N, p.wsplit_b[k], K, c0, nb, stage,
+                                              [&](int m, int col, float v0, float v1) {
+                                                const int64_t u = u_s[m];
+                                                if (u >= 0) {
+                                                  if (col < d) red_add2(p.gum + u * d + col, v0, v1);
+                                                  else red_add2(p.gim + i_s[m] * d + (col - d), v0, v1);
+                                                }
+                                              });
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+template <int TM>
+size_t mma_smem_bytes(TileParams& p) {
+  int off = 0;
+  const bool has_mlp = p.type != NCF_GMF;
+  for (int k = 0; k <= p.L; ++k) {
+    p.smem_off[k] = off;
+    if (has_mlp) off += TM * (p.W[k] + 8);
+  }
+  p.gmf_off = off;
+  off += 2 * TM * p.f;
+  off = (off + 3) & ~3;
+  p.stage_off = off;
+  off += 2 * kStageFloats;
+  p.misc_off = off;
+  off += 2 * TM + 4 * TM;
+  return (size_t)off * sizeof(float);
+}
+
+template <int PASSES, int TM, bool TRAIN>
+int launch_mma(TileParams& p, cudaStream_t st) {
+  const size_t smem = mma_smem_bytes<TM>(p);
+  auto kern = ncf_mma_tile_kernel<PASSES, TM, TRAIN>;
+  NCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (p.B + TM - 1) / TM;
+  int per_sm = (int)(225 * 1024 / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  int64_t grid = (int64_t)ncf::num_sms() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(int)grid, kThreads, smem, st>>>(p);
+  NCF_LAUNCH_CHECK("ncf_mma_tile_kernel");
+  return NCF_OK;
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+}  // namespace
+
+namespace ncf {
+
+// 0 = not eligible, else the tile height (64 or 32).
+int mma_tile_rows(const TileParams& p_in) {
+  if (p_in.type == NCF_GMF) return 0;          // no tower: the generic kernel is already a pure gather
+  if ((p_in.f & 7) != 0) return 0;
+  TileParams p = p_in;
+  if (mma_smem_bytes<64>(p) <= kSmemLimit) return 64;
+  if (mma_smem_bytes<32>(p) <= kSmemLimit) return 32;
+  return 0;
+}
+
+int64_t mma_split_floats(const TileParams& p) {
+  int64_t n = 0;
+  for (int k = 0; k < p.L; ++k) n += 2 * 2 * (int64_t)p.W[k] * p.W[k + 1];
+  return n;
+}
+
+// ws: mma_split_floats(p) floats.  Fills p.wsplit_f / p.wsplit_b and launches the split.
+int mma_prepare_weights(TileParams& p, float* ws, cudaStream_t st) {
+  for (int k = 0; k < p.L; ++k) {
+    const int64_t n = 2 * (int64_t)p.W[k] * p.W[k + 1];
+    p.wsplit_f[k] = ws;
+    p.wsplit_b[k] = ws + n;
+    ws += 2 * n;
+  }
+  split_weights_kernel<<<dim3(32, p.L), 256, 0, st>>>(p);
+  NCF_LAUNCH_CHECK("split_weights_kernel");
+  return NCF_OK;
+}
+
+int launch_mma_forward(TileParams& p, int passes, cudaStream_t st) {
+  const int tm = mma_tile_rows(p);
+  if (tm == 64) return passes == 3 ? launch_mma<3, 64, false>(p, st) : launch_mma<1, 64, false>(p, st);
+  if (tm == 32) return passes == 3 ? launch_mma<3, 32, false>(p, st) : launch_mma<1, 32, false>(p, st);
+  set_error("model not eligible for the mma tile kernel");
+  return NCF_ERR_ARG;
+}
+
+int launch_mma_train(TileParams& p, int passes, cudaStream_t st) {
+  const int tm = mma_tile_rows(p);
+  if (tm == 64) return passes == 3 ? launch_mma<3, 64, true>(p, st) : launch_mma<1, 64, true>(p, st);
+  if (tm == 32) return passes == 3 ? launch_mma<3, 32, true>(p, st) : launch_mma<1, 32, true>(p, st);
+  set_error("model not eligible for the mma tile kernel");
+  return NCF_ERR_ARG;
+}
+
+}  // namespace ncf

@@ -30,6 +30,9 @@ struct TileParams {
   // HBM scratch of per-sample activations / deltas (generic path)
   float* act[NCF_MAX_LAYERS + 1];    // act[k],   k = 1..L-1 : [B, W[k]]
   float* delta[NCF_MAX_LAYERS + 1];  // delta[k], k = 1..L   : [B, W[k]]
+  // pre-split (hi, lo) TF32 weights for the mma path: forward operand and transposed operand
+  float* wsplit_f[NCF_MAX_LAYERS];
+  float* wsplit_b[NCF_MAX_LAYERS];
   // shared-memory layout (float offsets), filled by the launcher
   int smem_off[NCF_MAX_LAYERS + 1];
   int gmf_off, stage_off, misc_off;
@@ -78,5 +81,13 @@ inline void fill_grad_params(TileParams& p, const NcfGrads* g) {
 
 int launch_generic_forward(TileParams& p, cudaStream_t st);
 int launch_generic_train(TileParams& p, cudaStream_t st);
+
+// tensor-pipe path (tile_mma.cu): eligible when mma_tile_rows(p) != 0
+int mma_tile_rows(const TileParams& p);
+int64_t mma_split_floats(const TileParams& p);
+int mma_prepare_weights(TileParams& p, float* ws, cudaStream_t st);
+int launch_mma_forward(TileParams& p, int passes, cudaStream_t st);
+int launch_mma_train(TileParams& p, int passes, cudaStream_t st);
+inline int tower_passes(const NcfModel* m) { return m->tower_math == NCF_MATH_TF32 ? 1 : 3; }
 
 }  // namespace ncf

@@ -35,6 +35,9 @@ class NCF(nn.Module):
             raise ValueError(f"num_layers must be in [1, {_lib.NCF_MAX_LAYERS}]")
         self.model_type = model_type
         self.dropout = dropout
+        # "fp32": tower contractions keep fp32 accuracy (3xTF32 / FMA) — the parity mode;
+        # "tf32": single-pass TF32 tensor-core math (opt-in, looser stated tolerance).
+        self.tower_math = "fp32"
         user_num, item_num = int(user_num), int(item_num)
         factor_num, num_layers = int(factor_num), int(num_layers)
         self.user_num, self.item_num = user_num, item_num
@@ -104,7 +107,8 @@ class NCF(nn.Module):
         return ops.model_struct(self.abi_type(), self.factor_num, self.num_layers, self.user_num,
                                 self.item_num, [t.detach() for t in tables],
                                 [(w.detach(), b.detach()) for w, b in lin],
-                                (self.predict_layer.weight.detach(), self.predict_layer.bias.detach()))
+                                (self.predict_layer.weight.detach(), self.predict_layer.bias.detach()),
+                                tower_math=self.tower_math)
 
     def _check_dropout(self):
         if self.training and self.dropout and self.dropout > 0:

@@ -15,6 +15,22 @@ from . import _lib
 from ._lib import NcfAdamHyper, NcfAdamState, NcfGrads, NcfModel, check, current_stream, ptr
 
 
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int):
+    """A per-device scratch buffer for inference calls (grown on demand, reused across calls on
+    the same stream; training owns its own workspace in FusedTrainStep)."""
+    if nbytes <= 0:
+        return None
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
 def tower_widths(factor_num: int, num_layers: int):
     """[f*2^L, f*2^(L-1), ..., f] — reference src/ncf/models.py:20-26."""
     return [factor_num << (num_layers - k) for k in range(num_layers + 1)]
@@ -36,12 +52,16 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+TOWER_MATH = {"fp32": 0, "tf32": 1}
+
+
 def model_struct(model_type: int, factor_num: int, num_layers: int, user_num: int, item_num: int,
-                 tables, linears, predict) -> NcfModel:
+                 tables, linears, predict, tower_math: str = "fp32") -> NcfModel:
     """tables = (user_gmf, item_gmf, user_mlp, item_mlp); linears = [(w, b)]*L; predict = (w, b)."""
     m = NcfModel()
     m.model_type, m.factor_num, m.num_layers = model_type, factor_num, num_layers
     m.mlp_dim = factor_num << (num_layers - 1)
+    m.tower_math = TOWER_MATH[tower_math]
     m.user_num, m.item_num = user_num, item_num
     m.embed_user_gmf, m.embed_item_gmf, m.embed_user_mlp, m.embed_item_mlp = (
         ptr(_f32(t, "table")) for t in tables)
@@ -106,8 +126,13 @@ def forward(m: NcfModel, user: torch.Tensor, item: torch.Tensor,
         raise _lib.NcfError("forward: user and item differ in length")
     if out is None:
         out = torch.empty(B, dtype=torch.float32, device=user.device)
+    ws_bytes = int(lib.ncf_forward_workspace_bytes(C.byref(m), B))
+    if ws_bytes < 0:
+        raise _lib.NcfError("ncf_forward_workspace_bytes: bad model")
+    ws = _workspace(user.device, ws_bytes)
     check(lib.ncf_forward(C.byref(m), ptr(_i64(user, "user")), ptr(_i64(item, "item")), B,
-                          ptr(_f32(out, "logits")), None, 0, current_stream()), "ncf_forward")
+                          ptr(_f32(out, "logits")), ptr(ws) if ws is not None else None, ws_bytes,
+                          current_stream()), "ncf_forward")
     return out
 
 
@@ -297,7 +322,9 @@ def eval_users(m: NcfModel, users: torch.Tensor, cands: torch.Tensor, k: int):
     ndcg = torch.empty(n, dtype=torch.float32, device=dev)
     topk = torch.empty(n, k, dtype=torch.int32, device=dev)
     scores = torch.empty(n, Cc, dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.ncf_eval_workspace_bytes(C.byref(m), n, Cc))
+    ws = _workspace(dev, ws_bytes)
     check(lib.ncf_eval_users(C.byref(m), ptr(_i64(users, "users")), ptr(_i64(cands, "cands")), n, Cc,
-                             k, ptr(hit), ptr(rank), ptr(ndcg), ptr(topk), ptr(scores), None, 0,
-                             current_stream()), "ncf_eval_users")
+                             k, ptr(hit), ptr(rank), ptr(ndcg), ptr(topk), ptr(scores), ptr(ws),
+                             ws_bytes, current_stream()), "ncf_eval_users")
     return hit, rank, ndcg, topk, scores

@@ -46,7 +46,7 @@ def test_version_error_string_and_pure_host_queries():
 
 def test_struct_layout_matches_header():
     from ncf_b200 import _lib
-    assert ctypes.sizeof(_lib.NcfModel) == 4 * 4 + 2 * 8 + 4 * 8 + 2 * 8 * 8 + 2 * 8
+    assert ctypes.sizeof(_lib.NcfModel) == 6 * 4 + 2 * 8 + 4 * 8 + 2 * 8 * 8 + 2 * 8
     assert ctypes.sizeof(_lib.NcfGrads) == 10 * 8
     assert ctypes.sizeof(_lib.NcfAdamState) == 13 * 8
     assert ctypes.sizeof(_lib.NcfAdamHyper) == 16
