@@ -22,9 +22,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -48,52 +46,54 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML (a thread, every 50 ms) during the timed
+    region — the same fields as the nvidia-smi clocks line of B200_PROFILING.md."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+        self.gpu, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
+        self._stop, self._thread, self._nvml = None, None, None
 
     def start(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
         except Exception:
-            self.proc = None
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
+                self._stop.wait(0.05)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path).read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.path)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        return out
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit),
+                "samples": len(s)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -23,11 +23,13 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = 8;
+constexpr int kThreads = 512;          // 16 warps: 4 per scheduler to hide the split / LDS latencies
+constexpr int kWarps = 16;
 constexpr int kStageRow = 48;          // floats per staged weight row: 2 k-steps x 16 + 16 pad
 constexpr int kStageRows = 128;        // output rows per staged block
 constexpr int kStageFloats = kStageRows * kStageRow;
+constexpr int kStages = 3;             // cp.async ring depth
+static_assert(kThreads == 4 * kStageRows, "staging maps one thread to one 16-byte piece of a row");
 
 __device__ __forceinline__ uint32_t f2tf32(float x) {
   uint32_t r;
@@ -35,15 +37,19 @@ __device__ __forceinline__ uint32_t f2tf32(float x) {
   return r;
 }
 
+// Activation split for 3xTF32.  The tensor core reads only the upper 19 bits of a tf32 operand
+// register (sign, 8 exponent, 10 mantissa bits), i.e. it truncates.  So hi is x itself (consumed as
+// trunc(x)), and lo = x - trunc(x) is exact in fp32 and in turn consumed truncated to 10 bits:
+// x*w = trunc(x)*w + lo*w with a relative defect <= 2^-21 — two full-rate instructions per element.
 struct Split {
   uint32_t hi, lo;
 };
 template <int PASSES>
 __device__ __forceinline__ Split split_tf32(float x) {
   Split s;
-  s.hi = f2tf32(x);
+  s.hi = __float_as_uint(x);
   s.lo = 0;
-  if (PASSES == 3) s.lo = f2tf32(x - __uint_as_float(s.hi));
+  if (PASSES == 3) s.lo = __float_as_uint(x - __uint_as_float(s.hi & 0xffffe000u));
   return s;
 }
 
@@ -122,59 +128,80 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
 
+  // Staging: thread (r = tid/4, quad = tid%4) copies the 16-byte piece `quad` of row r of each
+  // k-step of the chunk — 512 threads cover the 128 rows exactly, no index arithmetic in the loop.
+  const int st_r = tid >> 2, st_q = tid & 3;
+  const bool st_on = st_r < nb;
+  const float* st_src = wsplit + ((int64_t)row0 + st_r) * 16 + st_q * 4;
+  const int64_t st_ks_stride = (int64_t)rows_total * 16;
+  const int st_dst = st_r * kStageRow + st_q * 4;
   auto load_chunk = [&](int c, float* buf) {
-    const int ks0 = c * 2, n_ks = min(2, nks - ks0);
-    const int total = n_ks * nb * 4;  // 16-byte pieces
-    for (int idx = tid; idx < total; idx += kThreads) {
-      const int quad = idx & 3, r = (idx >> 2) % nb, ks = (idx >> 2) / nb;
-      cp_async16(buf + r * kStageRow + ks * 16 + quad * 4,
-                 wsplit + ((int64_t)(ks0 + ks) * rows_total + row0 + r) * 16 + quad * 4);
+    if (st_on) {
+      const float* src = st_src + (int64_t)(c * 2) * st_ks_stride;
+      cp_async16(buf + st_dst, src);
+      if (c * 2 + 1 < nks) cp_async16(buf + st_dst + 16, src + st_ks_stride);
     }
     cp_async_commit();
   };
 
+  // per-thread fragment bases: A row g of m-tile 0 at column 2t; B row (wn*8*NT + g) at 4t
+  const float* a_base = A + (wm * 16 * MT + g) * lda + 2 * t;
+  const int a_row8 = 8 * lda, a_tile = 16 * lda;
+  const int b_off = (wn * 8 * NT + g) * kStageRow + t * 4;
+
+  // 3-deep ring, one barrier per chunk: the barrier that publishes chunk c also certifies that
+  // every warp is done with chunk c-1, whose buffer the load of chunk c+2 then overwrites.
   load_chunk(0, stage);
+  if (nchunks > 1) load_chunk(1, stage + kStageFloats);
+  int slot = 0;
   for (int c = 0; c < nchunks; ++c) {
-    float* buf = stage + (c & 1) * kStageFloats;
-    if (c + 1 < nchunks) {
-      load_chunk(c + 1, stage + ((c + 1) & 1) * kStageFloats);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const float* buf = stage + slot * kStageFloats + b_off;
+    if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    if (c + 2 < nchunks) {
+      const int s2 = slot + 2 >= kStages ? slot + 2 - kStages : slot + 2;
+      load_chunk(c + 2, stage + s2 * kStageFloats);
+    }
+    slot = slot + 1 == kStages ? 0 : slot + 1;
     const int n_ks = active ? min(2, nks - c * 2) : 0;
     for (int ks = 0; ks < n_ks; ++ks) {
-      const int k0 = (c * 2 + ks) * 8;
+      const float* ap = a_base + (c * 2 + ks) * 8;
       uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        const float* ap = A + (wm * 16 * MT + i * 16 + g) * lda + k0 + 2 * t;
-        const float2 x0 = *reinterpret_cast<const float2*>(ap);
-        const float2 x1 = *reinterpret_cast<const float2*>(ap + 8 * lda);
+        const float2 x0 = *reinterpret_cast<const float2*>(ap + i * a_tile);
+        const float2 x1 = *reinterpret_cast<const float2*>(ap + i * a_tile + a_row8);
         const Split s0 = split_tf32<PASSES>(x0.x), s2 = split_tf32<PASSES>(x0.y);
         const Split s1 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
         ahi[i][0] = s0.hi; ahi[i][1] = s1.hi; ahi[i][2] = s2.hi; ahi[i][3] = s3.hi;
         alo[i][0] = s0.lo; alo[i][1] = s1.lo; alo[i][2] = s2.lo; alo[i][3] = s3.lo;
       }
+      uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(buf + (wn * 8 * NT + j * 8 + g) * kStageRow +
-                                                          ks * 16 + t * 4);
-        const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
-        const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-          if (PASSES == 3) {
-            mma_tf32(acc[i][j], alo[i], bh0, bh1);
-            mma_tf32(acc[i][j], ahi[i], bl0, bl1);
-          }
-          mma_tf32(acc[i][j], ahi[i], bh0, bh1);
-        }
+        const float4 b = *reinterpret_cast<const float4*>(buf + j * 8 * kStageRow + ks * 16);
+        bh[j][0] = __float_as_uint(b.x); bh[j][1] = __float_as_uint(b.y);
+        bl[j][0] = __float_as_uint(b.z); bl[j][1] = __float_as_uint(b.w);
       }
+      // Issue order: MT*NT independent accumulators per pass, so consecutive MMAs never depend
+      // on each other (the warp issues in order; a dependent chain would expose the MMA latency).
+      if (PASSES == 3) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], alo[i], bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bl[j][0], bl[j][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bh[j][0], bh[j][1]);
     }
-    __syncthreads();
   }
+  __syncthreads();  // stage buffers are free again; also orders the epilogue after all A reads
   if (!active) return;
 #pragma unroll
   for (int i = 0; i < MT; ++i)
@@ -194,16 +221,17 @@ __device__ __forceinline__ void gemm_act_weight_block(const float* A, int lda, i
                                                       int nb, float* stage, Epi epi) {
   // warps along n: up to 4 (8 when TM == 32 and nb allows); the rest along m
   constexpr int MTILES = TM / 16;
+  // (MT, NT, warps along n): 16 warps = (TM / (16*MT)) x WN when the block is large enough
   if (TM == 64) {
-    if (nb == 128) gemm_act_weight<PASSES, 2, 4>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
-    else if (nb == 64) gemm_act_weight<PASSES, 2, 2>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
-    else if (nb == 32) gemm_act_weight<PASSES, 2, 1>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    if (nb == 128) gemm_act_weight<PASSES, 2, 2>(A, lda, len, wsplit, rows_total, row0, nb, 8, TM, stage, epi);
+    else if (nb == 64) gemm_act_weight<PASSES, 2, 1>(A, lda, len, wsplit, rows_total, row0, nb, 8, TM, stage, epi);
+    else if (nb == 32) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
     else if (nb == 16) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 2, TM, stage, epi);
     else gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 1, TM, stage, epi);
   } else {
     static_assert(MTILES == 2 || MTILES == 4, "TM must be 32 or 64");
-    if (nb == 128) gemm_act_weight<PASSES, 1, 4>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
-    else if (nb == 64) gemm_act_weight<PASSES, 1, 2>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
+    if (nb == 128) gemm_act_weight<PASSES, 1, 2>(A, lda, len, wsplit, rows_total, row0, nb, 8, TM, stage, epi);
+    else if (nb == 64) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 8, TM, stage, epi);
     else if (nb == 32) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 4, TM, stage, epi);
     else if (nb == 16) gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 2, TM, stage, epi);
     else gemm_act_weight<PASSES, 1, 1>(A, lda, len, wsplit, rows_total, row0, nb, 1, TM, stage, epi);
@@ -229,40 +257,46 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd,
       for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    const float* d_base = D + t * ldd + n0 + 2 * g;   // MMA rows g, g+8 <-> n, n+1
+    const float* h_base = H + t * ldh + c0 + 2 * g;   // tile 2jj col g <-> c, tile 2jj+1 col g <-> c+1
     for (int m0 = 0; m0 < TM; m0 += 8) {
       uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        const int n = n0 + i * 16 + 2 * g;  // MMA rows g, g+8 <-> n, n+1
         float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-        if (n < N) {
-          x0 = *reinterpret_cast<const float2*>(D + (m0 + t) * ldd + n);
-          x1 = *reinterpret_cast<const float2*>(D + (m0 + t + 4) * ldd + n);
+        if (n0 + i * 16 + 2 * g < N) {
+          x0 = *reinterpret_cast<const float2*>(d_base + m0 * ldd + i * 16);
+          x1 = *reinterpret_cast<const float2*>(d_base + (m0 + 4) * ldd + i * 16);
         }
         const Split s0 = split_tf32<PASSES>(x0.x), s1 = split_tf32<PASSES>(x0.y);
         const Split s2 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
         ahi[i][0] = s0.hi; ahi[i][1] = s1.hi; ahi[i][2] = s2.hi; ahi[i][3] = s3.hi;
         alo[i][0] = s0.lo; alo[i][1] = s1.lo; alo[i][2] = s2.lo; alo[i][3] = s3.lo;
       }
+      uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
       for (int jj = 0; jj < NT / 2; ++jj) {
-        const int c = c0 + jj * 16 + 2 * g;  // tile 2jj col g <-> c, tile 2jj+1 col g <-> c+1
-        const float2 y0 = *reinterpret_cast<const float2*>(H + (m0 + t) * ldh + c);
-        const float2 y1 = *reinterpret_cast<const float2*>(H + (m0 + t + 4) * ldh + c);
+        const float2 y0 = *reinterpret_cast<const float2*>(h_base + m0 * ldh + jj * 16);
+        const float2 y1 = *reinterpret_cast<const float2*>(h_base + (m0 + 4) * ldh + jj * 16);
         const Split e0 = split_tf32<PASSES>(y0.x), o0 = split_tf32<PASSES>(y0.y);
         const Split e1 = split_tf32<PASSES>(y1.x), o1 = split_tf32<PASSES>(y1.y);
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-          if (PASSES == 3) {
-            mma_tf32(acc[i][2 * jj], alo[i], e0.hi, e1.hi);
-            mma_tf32(acc[i][2 * jj], ahi[i], e0.lo, e1.lo);
-            mma_tf32(acc[i][2 * jj + 1], alo[i], o0.hi, o1.hi);
-            mma_tf32(acc[i][2 * jj + 1], ahi[i], o0.lo, o1.lo);
-          }
-          mma_tf32(acc[i][2 * jj], ahi[i], e0.hi, e1.hi);
-          mma_tf32(acc[i][2 * jj + 1], ahi[i], o0.hi, o1.hi);
-        }
+        bh[2 * jj][0] = e0.hi; bh[2 * jj][1] = e1.hi; bl[2 * jj][0] = e0.lo; bl[2 * jj][1] = e1.lo;
+        bh[2 * jj + 1][0] = o0.hi; bh[2 * jj + 1][1] = o1.hi; bl[2 * jj + 1][0] = o0.lo; bl[2 * jj + 1][1] = o1.lo;
       }
+      if (PASSES == 3) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], alo[i], bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bl[j][0], bl[j][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bh[j][0], bh[j][1]);
     }
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
@@ -282,8 +316,11 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd,
 template <int PASSES, int TM>
 __device__ __forceinline__ void wgrad_dispatch(const float* D, int ldd, int N, const float* H, int ldh,
                                                int K, float* gw) {
-  if ((N & 31) == 0 && (K & 31) == 0) gemm_wgrad<PASSES, TM, 2, 4>(D, ldd, N, H, ldh, K, gw);
-  else gemm_wgrad<PASSES, TM, 1, 2>(D, ldd, N, H, ldh, K, gw);
+  // 32x32 tiles when there are enough of them to occupy every warp, 16x16 tiles otherwise
+  if ((N & 31) == 0 && (K & 31) == 0 && (N >> 5) * (K >> 5) >= kWarps)
+    gemm_wgrad<PASSES, TM, 2, 4>(D, ldd, N, H, ldh, K, gw);
+  else
+    gemm_wgrad<PASSES, TM, 1, 2>(D, ldd, N, H, ldh, K, gw);
 }
 
 // ---- the tile kernel --------------------------------------------------------------------------------
@@ -524,7 +561,7 @@ size_t mma_smem_bytes(TileParams& p) {
   off += 2 * TM * p.f;
   off = (off + 3) & ~3;
   p.stage_off = off;
-  off += 2 * kStageFloats;
+  off += kStages * kStageFloats;
   p.misc_off = off;
   off += 2 * TM + 4 * TM;
   return (size_t)off * sizeof(float);

@@ -16,6 +16,7 @@ import torch
 
 SHAPES = {
     # name: (user_num, item_num, total interactions incl. the held-out one per user, seed)
+    "tiny": (400, 300, 14_000, 20250602),        # test-sized
     "ml100k": (943, 1682, 100_000, 20250603),
     "ml1m": (6040, 3706, 1_000_209, 20250604),
     "ml20m": (138_493, 26_744, 20_000_263, 20250605),
