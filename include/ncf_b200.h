@@ -184,6 +184,11 @@ int ncf_backward(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* 
  * equivalent); consumes and re-zeroes g, increments *s->step.
  * ncf_adam_flush: replays pending zero-gradient steps for every row (call before reading weights).
  * ncf_sgd_step: optim.SGD(lr).step() (reference scripts/train_neumf.py:88), no momentum. */
+/* ncf_mark_rows: registers the distinct (user, item) rows of a batch in g's touched lists — the
+ * dedup the optimisers iterate over.  Every optimiser step must be preceded by ncf_adam_prepare
+ * (Adam; it marks and catches up) or ncf_mark_rows (SGD) on the same batch. */
+int ncf_mark_rows(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* user,
+                  const int64_t* item, int64_t B, void* stream);
 /* ncf_adam_prepare: call BEFORE ncf_train_step_grads of the same batch.  Registers the batch's
  * distinct rows in g's touched lists and replays their pending zero-gradient steps, so that the
  * forward reads the rows exactly as the reference's dense Adam would have left them. */

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ncf_train_workspace_bytes": (_i64, [_P(NcfModel), _i64]),
     "ncf_train_step_grads": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _vp, _fl, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ncf_backward": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "ncf_mark_rows": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _i64, _vp]),
     "ncf_adam_prepare": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp, _vp, _i64, _vp]),
     "ncf_adam_step": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
     "ncf_adam_flush": (C.c_int, [_P(NcfModel), _P(NcfAdamState), NcfAdamHyper, _vp]),

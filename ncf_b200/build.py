@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("NCF_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -334,6 +334,26 @@ extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdam
   return NCF_OK;
 }
 
+static int launch_mark(const NcfModel* m, const NcfGrads* g, const int64_t* user,
+                       const int64_t* item, int64_t B, cudaStream_t st) {
+  int64_t blocks = (B + 255) / 256;
+  if (blocks > 4 * ncf::num_sms()) blocks = 4 * ncf::num_sms();
+  mark_rows_kernel<<<(int)blocks, 256, 0, st>>>(user, item, B, m->user_num, m->item_num,
+                                               g->user_flag, g->item_flag, g->user_list,
+                                               g->item_list, g->touched_count);
+  NCF_LAUNCH_CHECK("mark_rows_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_mark_rows(const NcfModel* m, const NcfGrads* g, const int64_t* user,
+                             const int64_t* item, int64_t B, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  NCF_REQUIRE(B > 0 && user && item, "ncf_mark_rows: empty batch or null pointer");
+  return launch_mark(m, g, user, item, B, (cudaStream_t)stream);
+}
+
 extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
                                 NcfAdamHyper h, const int64_t* user, const int64_t* item, int64_t B,
                                 void* stream) {
@@ -343,12 +363,7 @@ extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfA
   if ((rc = check_state(m, s)) != NCF_OK) return rc;
   NCF_REQUIRE(B > 0 && user && item, "ncf_adam_prepare: empty batch or null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (B + 255) / 256;
-  if (blocks > 4 * ncf::num_sms()) blocks = 4 * ncf::num_sms();
-  mark_rows_kernel<<<(int)blocks, 256, 0, st>>>(user, item, B, m->user_num, m->item_num,
-                                               g->user_flag, g->item_flag, g->user_list,
-                                               g->item_list, g->touched_count);
-  NCF_LAUNCH_CHECK("mark_rows_kernel");
+  if ((rc = launch_mark(m, g, user, item, B, st)) != NCF_OK) return rc;
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);

@@ -231,11 +231,6 @@ __global__ void __launch_bounds__(kThreads) ncf_tile_kernel(const TileParams p) 
       }
       atomicAdd(&p.gt[p.pw_off + c], s);
     }
-    if (tid < TM && u_s[tid] >= 0) {
-      const int64_t u = u_s[tid], it = i_s[tid];
-      if (atomicExch(&p.uflag[u], 1) == 0) p.ulist[atomicAdd(&p.tcount[0], 1)] = u;
-      if (atomicExch(&p.iflag[it], 1) == 0) p.ilist[atomicAdd(&p.tcount[1], 1)] = it;
-    }
     __syncthreads();  // hL reads above complete before delta_L overwrites it
 
     // ---- GMF branch backward: scatter row gradients --------------------------------------------

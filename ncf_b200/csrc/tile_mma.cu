@@ -21,6 +21,30 @@
 #include "common.cuh"
 #include "tile_params.cuh"
 
+#ifdef NCF_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define NCF_PHASE(i)                                                            \
+  do {                                                                          \
+    __syncthreads();                                                            \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+      const long long now = clock64();                                          \
+      g_phase_cycles[i] += (unsigned long long)(now - phase_t0);                \
+      phase_t0 = now;                                                           \
+    }                                                                           \
+  } while (0)
+extern "C" int ncf_debug_phase_cycles(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(g_phase_cycles));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#else
+#define NCF_PHASE(i) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = 512;          // 16 warps: 4 per scheduler to hide the split / LDS latencies
@@ -29,6 +53,9 @@ constexpr int kStageRow = 48;          // floats per staged weight row: 2 k-step
 constexpr int kStageRows = 128;        // output rows per staged block
 constexpr int kStageFloats = kStageRows * kStageRow;
 constexpr int kStages = 3;             // cp.async ring depth
+// Activation row stride = width + 4 floats: stride % 32 == 4 makes the 8 rows of an ldmatrix
+// phase hit 8 distinct 16-byte bank groups, and rows 2t apart (wgrad operand loads) 32 bytes apart.
+constexpr int kActPad = 4;
 static_assert(kThreads == 4 * kStageRows, "staging maps one thread to one 16-byte piece of a row");
 
 __device__ __forceinline__ uint32_t f2tf32(float x) {
@@ -72,14 +99,25 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void red_add2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // ---- pre-split weights ---------------------------------------------------------------------------
 // For a GEMM with `rows` output rows and contraction length `len` (multiple of 8), element
-// (r, c) lands at  [c/8][r][ ((c%8)/2)*4 + (c%2) ]  (hi)  and  +2 (lo): one 16-float record per
-// (k-step, row) holding the four (k, k+1) pairs as [hi0, hi1, lo0, lo1].
+// (r, c) lands at  [c/8][r][ (c%4)*4 + (c%8)/4 ]  (hi)  and  +2 (lo): one 16-float record per
+// (k-step, row); lane t reads its B fragment [hi(k=t), hi(k=t+4), lo(k=t), lo(k=t+4)] as one float4.
 __global__ void split_weights_kernel(const TileParams p) {
   const int k = blockIdx.y;
   if (k >= p.L) return;
@@ -93,12 +131,12 @@ __global__ void split_weights_kernel(const TileParams p) {
     const float hi = __uint_as_float(f2tf32(x));
     const float lo = __uint_as_float(f2tf32(x - hi));
     {  // forward operand: rows = n, contraction = c
-      float* d = wf + ((int64_t)(c >> 3) * N + n) * 16 + ((c & 7) >> 1) * 4 + (c & 1);
+      float* d = wf + ((int64_t)(c >> 3) * N + n) * 16 + (c & 3) * 4 + ((c >> 2) & 1);
       d[0] = hi;
       d[2] = lo;
     }
     {  // backward operand: rows = c, contraction = n
-      float* d = wb + ((int64_t)(n >> 3) * K + c) * 16 + ((n & 7) >> 1) * 4 + (n & 1);
+      float* d = wb + ((int64_t)(n >> 3) * K + c) * 16 + (n & 3) * 4 + ((n >> 2) & 1);
       d[0] = hi;
       d[2] = lo;
     }
@@ -144,10 +182,51 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
     cp_async_commit();
   };
 
-  // per-thread fragment bases: A row g of m-tile 0 at column 2t; B row (wn*8*NT + g) at 4t
-  const float* a_base = A + (wm * 16 * MT + g) * lda + 2 * t;
-  const int a_row8 = 8 * lda, a_tile = 16 * lda;
-  const int b_off = (wn * 8 * NT + g) * kStageRow + t * 4;
+  // Per-thread fragment addresses (32-bit shared-window addresses so that every access in the
+  // loop is base register + immediate).  A fragments come from ldmatrix.x4 on the fp32 tile
+  // viewed as 8x(16 byte) rows: lane l supplies row (l%8) + 8*((l/8)%2) at column 4*(l/16), and
+  // receives a0..a3 = (g,t), (g+8,t), (g,t+4), (g+8,t+4) — exactly the m16n8k8 TF32 A layout.
+  const uint32_t a_sh = (uint32_t)__cvta_generic_to_shared(A) +
+                        4u * ((wm * 16 * MT + (lane & 7) + 8 * ((lane >> 3) & 1)) * lda + 4 * (lane >> 4));
+  const uint32_t a_tile = 64u * lda;  // 16 rows, in bytes
+  const uint32_t b_sh0 = (uint32_t)__cvta_generic_to_shared(stage) +
+                         4u * ((wn * 8 * NT + g) * kStageRow + t * 4);
+
+  auto k_step = [&](uint32_t a_addr, uint32_t b_addr) {
+    uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      ldmatrix_x4(ahi[i], a_addr + i * a_tile);
+      if (PASSES == 3) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          alo[i][q] = __float_as_uint(__uint_as_float(ahi[i][q]) - __uint_as_float(ahi[i][q] & 0xffffe000u));
+      }
+    }
+    uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float4 b = lds128(b_addr + j * (8 * kStageRow * 4));
+      bh[j][0] = __float_as_uint(b.x); bh[j][1] = __float_as_uint(b.y);
+      bl[j][0] = __float_as_uint(b.z); bl[j][1] = __float_as_uint(b.w);
+    }
+    // Issue order: MT*NT independent accumulators per pass, so consecutive MMAs never depend on
+    // each other (the warp issues in order; a dependent chain would expose the MMA latency).
+    if (PASSES == 3) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], alo[i], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bl[j][0], bl[j][1]);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bh[j][0], bh[j][1]);
+  };
 
   // 3-deep ring, one barrier per chunk: the barrier that publishes chunk c also certifies that
   // every warp is done with chunk c-1, whose buffer the load of chunk c+2 then overwrites.
@@ -155,7 +234,7 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
   if (nchunks > 1) load_chunk(1, stage + kStageFloats);
   int slot = 0;
   for (int c = 0; c < nchunks; ++c) {
-    const float* buf = stage + slot * kStageFloats + b_off;
+    const uint32_t b_addr = b_sh0 + slot * (kStageFloats * 4);
     if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     if (c + 2 < nchunks) {
@@ -163,42 +242,10 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
       load_chunk(c + 2, stage + s2 * kStageFloats);
     }
     slot = slot + 1 == kStages ? 0 : slot + 1;
-    const int n_ks = active ? min(2, nks - c * 2) : 0;
-    for (int ks = 0; ks < n_ks; ++ks) {
-      const float* ap = a_base + (c * 2 + ks) * 8;
-      uint32_t ahi[MT][4], alo[MT][4];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const float2 x0 = *reinterpret_cast<const float2*>(ap + i * a_tile);
-        const float2 x1 = *reinterpret_cast<const float2*>(ap + i * a_tile + a_row8);
-        const Split s0 = split_tf32<PASSES>(x0.x), s2 = split_tf32<PASSES>(x0.y);
-        const Split s1 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
-        ahi[i][0] = s0.hi; ahi[i][1] = s1.hi; ahi[i][2] = s2.hi; ahi[i][3] = s3.hi;
-        alo[i][0] = s0.lo; alo[i][1] = s1.lo; alo[i][2] = s2.lo; alo[i][3] = s3.lo;
-      }
-      uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(buf + j * 8 * kStageRow + ks * 16);
-        bh[j][0] = __float_as_uint(b.x); bh[j][1] = __float_as_uint(b.y);
-        bl[j][0] = __float_as_uint(b.z); bl[j][1] = __float_as_uint(b.w);
-      }
-      // Issue order: MT*NT independent accumulators per pass, so consecutive MMAs never depend
-      // on each other (the warp issues in order; a dependent chain would expose the MMA latency).
-      if (PASSES == 3) {
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], alo[i], bh[j][0], bh[j][1]);
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-          for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bl[j][0], bl[j][1]);
-      }
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ahi[i], bh[j][0], bh[j][1]);
+    if (active) {
+      const uint32_t a_addr = a_sh + c * 64;  // 2 k-steps x 8 floats
+      k_step(a_addr, b_addr);
+      if (c * 2 + 1 < nks) k_step(a_addr + 32, b_addr + 64);
     }
   }
   __syncthreads();  // stage buffers are free again; also orders the epilogue after all A reads
@@ -257,8 +304,10 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd,
       for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-    const float* d_base = D + t * ldd + n0 + 2 * g;   // MMA rows g, g+8 <-> n, n+1
-    const float* h_base = H + t * ldh + c0 + 2 * g;   // tile 2jj col g <-> c, tile 2jj+1 col g <-> c+1
+    // k-slot t <-> sample row m0 + 2t, slot t+4 <-> m0 + 2t + 1 (any bijection works as long as A
+    // and B agree; this one keeps the four rows of a half-warp 8 banks apart)
+    const float* d_base = D + 2 * t * ldd + n0 + 2 * g;   // MMA rows g, g+8 <-> n, n+1
+    const float* h_base = H + 2 * t * ldh + c0 + 2 * g;   // tile 2jj col g <-> c, tile 2jj+1 col g <-> c+1
     for (int m0 = 0; m0 < TM; m0 += 8) {
       uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
@@ -266,7 +315,7 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd,
         float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
         if (n0 + i * 16 + 2 * g < N) {
           x0 = *reinterpret_cast<const float2*>(d_base + m0 * ldd + i * 16);
-          x1 = *reinterpret_cast<const float2*>(d_base + (m0 + 4) * ldd + i * 16);
+          x1 = *reinterpret_cast<const float2*>(d_base + (m0 + 1) * ldd + i * 16);
         }
         const Split s0 = split_tf32<PASSES>(x0.x), s1 = split_tf32<PASSES>(x0.y);
         const Split s2 = split_tf32<PASSES>(x1.x), s3 = split_tf32<PASSES>(x1.y);
@@ -277,7 +326,7 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ D, int ldd,
 #pragma unroll
       for (int jj = 0; jj < NT / 2; ++jj) {
         const float2 y0 = *reinterpret_cast<const float2*>(h_base + m0 * ldh + jj * 16);
-        const float2 y1 = *reinterpret_cast<const float2*>(h_base + (m0 + 4) * ldh + jj * 16);
+        const float2 y1 = *reinterpret_cast<const float2*>(h_base + (m0 + 1) * ldh + jj * 16);
         const Split e0 = split_tf32<PASSES>(y0.x), o0 = split_tf32<PASSES>(y0.y);
         const Split e1 = split_tf32<PASSES>(y1.x), o1 = split_tf32<PASSES>(y1.y);
         bh[2 * jj][0] = e0.hi; bh[2 * jj][1] = e1.hi; bl[2 * jj][0] = e0.lo; bl[2 * jj][1] = e1.lo;
@@ -339,13 +388,17 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
   float* ls_s = dl_s + TM;
   int64_t* u_s = reinterpret_cast<int64_t*>(ls_s + TM);
   int64_t* i_s = u_s + TM;
+  float* pg_s = reinterpret_cast<float*>(i_s + TM);  // [predict_size] predict-weight gradient of the tile
   auto act = [&](int k) { return smem + p.smem_off[k]; };
-  auto lda = [&](int k) { return p.W[k] + 8; };
+  auto lda = [&](int k) { return p.W[k] + kActPad; };
 
   const int64_t ntiles = (p.B + TM - 1) / TM;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t base = tile * TM;
     __syncthreads();
+#ifdef NCF_PHASE_TIMING
+    long long phase_t0 = clock64();
+#endif
     if (tid < TM) {
       const int64_t b = base + tid;
       int64_t u = -1, it = -1;
@@ -360,6 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
     __syncthreads();
 
     // ---- gather (one warp per sample row; 16-byte coalesced loads) -------------------------------
+    // cp.async: every 16-byte piece of the warp's rows is in flight before anything is waited on
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int m = warp + kWarps * i;
@@ -370,22 +424,30 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
         const float* ru = p.eum + (ok ? u : 0) * d;
         const float* ri = p.eim + (ok ? it : 0) * d;
         for (int c = lane * 4; c < d; c += 128) {
-          const float4 a = ok ? ldg4(ru + c) : make_float4(0, 0, 0, 0);
-          const float4 b4 = ok ? ldg4(ri + c) : make_float4(0, 0, 0, 0);
-          *reinterpret_cast<float4*>(x + c) = a;
-          *reinterpret_cast<float4*>(x + d + c) = b4;
+          if (ok) {
+            cp_async16(x + c, ru + c);
+            cp_async16(x + d + c, ri + c);
+          } else {
+            *reinterpret_cast<float4*>(x + c) = make_float4(0, 0, 0, 0);
+            *reinterpret_cast<float4*>(x + d + c) = make_float4(0, 0, 0, 0);
+          }
         }
       }
       if (has_gmf) {
         const float* ru = p.eug + (ok ? u : 0) * f;
         const float* ri = p.eig + (ok ? it : 0) * f;
-        for (int c = lane; c < f; c += 32) {
-          gu_s[m * f + c] = ok ? __ldg(ru + c) : 0.f;
-          gi_s[m * f + c] = ok ? __ldg(ri + c) : 0.f;
+        for (int c = lane * 4; c < 2 * f; c += 128) {  // f % 8 == 0: 16-byte pieces never straddle
+          float* dst = (c < f) ? gu_s + m * f + c : gi_s + m * f + (c - f);
+          const float* src = (c < f) ? ru + c : ri + (c - f);
+          if (ok) cp_async16(dst, src);
+          else *reinterpret_cast<float4*>(dst) = make_float4(0, 0, 0, 0);
         }
       }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    NCF_PHASE(0);  // indices + gather
 
     // ---- tower forward ------------------------------------------------------------------------------
     if (has_mlp) {
@@ -406,8 +468,9 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
       }
     }
     __syncthreads();
+    NCF_PHASE(1);  // tower forward
 
-    // ---- predict layer + loss -------------------------------------------------------------------------
+    // ---- predict layer: one warp per sample row computes the logit ------------------------------------------
     const float* hL = act(L);
     const int ldL = lda(L);
     const int fl = p.W[L];
@@ -415,45 +478,50 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int m = warp + kWarps * i;
-      const int64_t b = base + m;
       float s = 0.f;
       if (has_gmf)
         for (int c = lane; c < f; c += 32) s = fmaf(__ldg(&p.pw[c]), gu_s[m * f + c] * gi_s[m * f + c], s);
       if (has_mlp)
         for (int c = lane; c < fl; c += 32) s = fmaf(__ldg(&p.pw[mlp_w_off + c]), hL[m * ldL + c], s);
       s = warp_sum(s);
-      if (lane == 0) {
-        float x = s + __ldg(p.pb);
-        const bool ok = (b < p.B) && u_s[m] >= 0;
-        if (b < p.B && u_s[m] == -2) x = __int_as_float(0x7fc00000);
-        if (b < p.B && p.logits != nullptr) p.logits[b] = x;
-        if (TRAIN) {
-          float dl = 0.f, ls = 0.f;
-          if (ok && p.dlogit_in != nullptr) {
-            dl = p.dlogit_in[b];
-          } else if (ok) {
-            const float y = p.label[b];
-            const float e = expf(-fabsf(x));
-            const float bce = fmaxf(x, 0.f) - x * y + log1pf(e);
-            const float sig = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
-            if (p.teacher != nullptr) {
-              const float df = x - p.teacher[b];
-              ls = p.alpha * bce + (1.f - p.alpha) * df * df;
-              dl = (p.alpha * (sig - y) + (1.f - p.alpha) * 2.f * df) * p.invB;
-            } else {
-              ls = bce;
-              dl = (sig - y) * p.invB;
-            }
+      if (lane == 0) ls_s[m] = s + __ldg(p.pb);
+    }
+    __syncthreads();
+    // ---- loss and dloss/dlogit: one thread per sample row ---------------------------------------------------------
+    if (tid < TM) {
+      const int m = tid;
+      const int64_t b = base + m;
+      float x = ls_s[m];
+      const bool ok = (b < p.B) && u_s[m] >= 0;
+      if (b < p.B && u_s[m] == -2) x = __int_as_float(0x7fc00000);  // out-of-range index: NaN
+      if (b < p.B && p.logits != nullptr) p.logits[b] = x;
+      if (TRAIN) {
+        float dl = 0.f, ls = 0.f;
+        if (ok && p.dlogit_in != nullptr) {
+          dl = p.dlogit_in[b];
+        } else if (ok) {
+          const float y = p.label[b];
+          const float e = expf(-fabsf(x));
+          const float bce = fmaxf(x, 0.f) - x * y + log1pf(e);
+          const float sig = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+          if (p.teacher != nullptr) {
+            const float df = x - p.teacher[b];
+            ls = p.alpha * bce + (1.f - p.alpha) * df * df;
+            dl = (p.alpha * (sig - y) + (1.f - p.alpha) * 2.f * df) * p.invB;
+          } else {
+            ls = bce;
+            dl = (sig - y) * p.invB;
           }
-          dl_s[m] = dl;
-          ls_s[m] = ls;
         }
+        dl_s[m] = dl;
+        ls_s[m] = ls;
       }
     }
     if (!TRAIN) continue;
+    for (int c = tid; c < p.predict_size; c += kThreads) pg_s[c] = 0.f;
     __syncthreads();
 
-    // ---- loss, predict-layer gradients, touched lists ------------------------------------------------------
+    // ---- loss, predict-layer gradients, GMF branch backward: one warp per sample row --------------------------------
     if (warp == 0) {
       float ls = 0.f, dsum = 0.f;
       for (int m = lane; m < TM; m += 32) { ls += ls_s[m]; dsum += dl_s[m]; }
@@ -464,38 +532,53 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
         atomicAdd(&p.gt[p.pb_off], dsum);
       }
     }
-    for (int c = tid; c < p.predict_size; c += kThreads) {
-      float s = 0.f;
-      if (has_gmf && c < f) {
-        for (int m = 0; m < TM; ++m) s = fmaf(dl_s[m], gu_s[m * f + c] * gi_s[m * f + c], s);
-      } else {
-        const int j = c - mlp_w_off;
-        for (int m = 0; m < TM; ++m) s = fmaf(dl_s[m], hL[m * ldL + j], s);
-      }
-      atomicAdd(&p.gt[p.pw_off + c], s);
-    }
-    if (tid < TM && u_s[tid] >= 0) {
-      const int64_t u = u_s[tid], it = i_s[tid];
-      if (atomicExch(&p.uflag[u], 1) == 0) p.ulist[atomicAdd(&p.tcount[0], 1)] = u;
-      if (atomicExch(&p.iflag[it], 1) == 0) p.ilist[atomicAdd(&p.tcount[1], 1)] = it;
-    }
-    __syncthreads();
-
-    // ---- GMF branch backward ---------------------------------------------------------------------------------
-    if (has_gmf) {
+    {
+      // lane c keeps the partial predict-weight gradient of columns c, c+32, ... over the warp's rows
+      float pg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         const int m = warp + kWarps * i;
-        const int64_t u = u_s[m], it = i_s[m];
-        if (u < 0) continue;
         const float dl = dl_s[m];
-        for (int c = lane; c < f; c += 32) {
-          const float w = __ldg(&p.pw[c]) * dl;
-          atomicAdd(&p.gug[u * f + c], w * gi_s[m * f + c]);
-          atomicAdd(&p.gig[it * f + c], w * gu_s[m * f + c]);
+        const int64_t u = u_s[m], it = i_s[m];
+        if (has_gmf) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            if (c < f) {
+              const float gu = gu_s[m * f + c], gi = gi_s[m * f + c];
+              pg[q] = fmaf(dl, gu * gi, pg[q]);
+              if (u >= 0) {
+                const float w = __ldg(&p.pw[c]) * dl;
+                atomicAdd(&p.gug[u * f + c], w * gi);
+                atomicAdd(&p.gig[it * f + c], w * gu);
+              }
+            }
+          }
         }
       }
+      if (has_gmf) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (lane + 32 * q < f) atomicAdd(&pg_s[lane + 32 * q], pg[q]);
+      }
+      if (has_mlp) {
+        float pm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int m = warp + kWarps * i;
+          const float dl = dl_s[m];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < fl) pm[q] = fmaf(dl, hL[m * ldL + lane + 32 * q], pm[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (lane + 32 * q < fl) atomicAdd(&pg_s[mlp_w_off + lane + 32 * q], pm[q]);
+      }
     }
+    __syncthreads();
+    for (int c = tid; c < p.predict_size; c += kThreads) atomicAdd(&p.gt[p.pw_off + c], pg_s[c]);
+    NCF_PHASE(2);  // predict, loss, predict grads, GMF scatter
 
     // ---- tower backward ----------------------------------------------------------------------------------------
     if (has_mlp) {
@@ -508,19 +591,29 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
         }
       }
       __syncthreads();
+      NCF_PHASE(3);  // GMF scatter + delta_L
       for (int k = L - 1; k >= 0; --k) {
         const int K = p.W[k], N = p.W[k + 1];
         const float* dn = act(k + 1);  // delta_{k+1} [TM][N]
         const int ldd = lda(k + 1);
         // bias gradient: column sums of delta_{k+1}
-        for (int n = tid; n < N; n += kThreads) {
-          float s = 0.f;
-          for (int m = 0; m < TM; ++m) s += dn[m * ldd + n];
-          atomicAdd(&p.gt[p.b_off[k] + n], s);
+        {
+          // thread (n, part) sums TM/parts rows of column n; parts = as many as the CTA can field
+          int parts = kThreads / N;
+          parts = parts > 16 ? 16 : (parts < 1 ? 1 : parts);
+          const int rows = (TM + parts - 1) / parts;
+          for (int idx = tid; idx < N * parts; idx += kThreads) {
+            const int n = idx % N, m0 = (idx / N) * rows;
+            float s = 0.f;
+            for (int m = m0; m < min(TM, m0 + rows); ++m) s += dn[m * ldd + n];
+            atomicAdd(&p.gt[p.b_off[k] + n], s);
+          }
         }
+        NCF_PHASE(4);  // bias gradients
         // weight gradient
         wgrad_dispatch<PASSES, TM>(dn, ldd, N, act(k), lda(k), K, p.gt + p.w_off[k]);
         __syncthreads();  // every read of H_k is done before it is overwritten by delta_k
+        NCF_PHASE(5 + min(k, 2));  // wgrad of layer k (5: k=0, 6: k=1, 7: k>=2)
         float* hk = act(k);
         const int ldh = lda(k);
         for (int c0 = 0; c0 < K; c0 += kStageRows) {
@@ -544,6 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncf_mma_tile_kernel(const TilePar
           }
         }
         __syncthreads();
+        NCF_PHASE(8 + min(k, 2));  // backward data of layer k (8: dX, 9: k=1, 10: k>=2)
       }
     }
   }
@@ -555,7 +649,7 @@ size_t mma_smem_bytes(TileParams& p) {
   const bool has_mlp = p.type != NCF_GMF;
   for (int k = 0; k <= p.L; ++k) {
     p.smem_off[k] = off;
-    if (has_mlp) off += TM * (p.W[k] + 8);
+    if (has_mlp) off += TM * (p.W[k] + kActPad);
   }
   p.gmf_off = off;
   off += 2 * TM * p.f;
@@ -563,7 +657,7 @@ size_t mma_smem_bytes(TileParams& p) {
   p.stage_off = off;
   off += kStages * kStageFloats;
   p.misc_off = off;
-  off += 2 * TM + 4 * TM;
+  off += 2 * TM + 4 * TM + ((p.predict_size + 3) & ~3);
   return (size_t)off * sizeof(float);
 }
 
@@ -592,7 +686,7 @@ namespace ncf {
 // 0 = not eligible, else the tile height (64 or 32).
 int mma_tile_rows(const TileParams& p_in) {
   if (p_in.type == NCF_GMF) return 0;          // no tower: the generic kernel is already a pure gather
-  if ((p_in.f & 7) != 0) return 0;
+  if (p_in.f < 8 || (p_in.f & (p_in.f - 1)) != 0) return 0;  // block shapes assume power-of-two widths
   TileParams p = p_in;
   if (mma_smem_bytes<64>(p) <= kSmemLimit) return 64;
   if (mma_smem_bytes<32>(p) <= kSmemLimit) return 32;

@@ -268,6 +268,13 @@ def backward(m: NcfModel, g: NcfGrads, user, item, dlogit, workspace: torch.Tens
 
 
 # ---- a10 ------------------------------------------------------------------------------------------------
+def mark_rows(m: NcfModel, g: NcfGrads, user, item):
+    """Registers the batch's distinct rows in the touched lists (SGD path; Adam uses adam_prepare)."""
+    check(_lib.load().ncf_mark_rows(C.byref(m), C.byref(g), ptr(_i64(user, "user")),
+                                    ptr(_i64(item, "item")), user.numel(), current_stream()),
+          "ncf_mark_rows")
+
+
 def adam_prepare(m: NcfModel, g: NcfGrads, s: NcfAdamState, user, item, lr, beta1=0.9, beta2=0.999,
                  eps=1e-8):
     """Registers the batch's rows and replays their pending zero-gradient Adam steps; must

@@ -74,6 +74,8 @@ class FusedTrainStep:
             # rows this batch reads must first catch up with the dense-Adam trajectory
             ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
                              self.betas[1], self.eps)
+        else:
+            ops.mark_rows(self._m, self._g, user, item)
         ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
                              self.loss_accum, self.workspace, logits_out)
         if self.optimizer == "adam":

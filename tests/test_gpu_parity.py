@@ -76,6 +76,7 @@ def test_fused_step_gradients_match_reference(name):
     ws = torch.empty(ops.train_workspace_bytes(m, B), dtype=torch.uint8, device=dev())
     loss = torch.zeros(1, dtype=torch.float64, device=dev())
     logits = torch.empty(B, device=dev())
+    ops.mark_rows(m, g.struct(), u, i)
     ops.train_step_grads(m, g.struct(), u, i, y, None, 1.0, loss, ws, logits)
     assert_close(logits.cpu().numpy(), z["logits0"], "logits")
     assert abs(loss.item() - z["loss"][0]) <= 2e-6 * abs(z["loss"][0])
