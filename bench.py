@@ -37,6 +37,22 @@ WORKLOADS = {
 METRIC, UNIT = "NeuMF train samples/s", "samples/s"
 
 
+def measured_tensor_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["bf16_tflops"])
+    return 1590.0
+
+
+def profile_traffic(kernel):
+    """DRAM bytes per launch of the kernel from the committed ncu capture (profiles/traffic.json),
+    or None when no capture of this kernel is on file."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        return json.loads(p.read_text()).get(kernel)
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -183,6 +199,7 @@ def run_ours(args):
     U, I = inter.user_num, inter.item_num
     torch.manual_seed(0)
     model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
+    model.tower_math = args.tower_math
     ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
     # every rank draws from its own slice of the epoch stream (weak scaling: B per GPU per step)
     stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=20250605)
@@ -233,7 +250,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * K * B / (ms_total * 1e-3)
-    launches_per_step = 7  # mark, catch-up, fused tile, tower wgrad, row Adam, tower Adam, finalize
+    launches_per_step = 7  # mark, catch-up, weight split, fused tile, row Adam, tower Adam, finalize
 
     # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
     phases = None
@@ -289,27 +306,66 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    peak, peak_src = measured_peaks()
+    hbm_peak, peak_src = measured_peaks()
+    tensor_peak = measured_tensor_peak()
     d = f << (L - 1)
     R = 2 * f + 2 * d
+    macs = sum((f << (L - k)) * (f << (L - k - 1)) for k in range(L)) + 2 * f   # tower + predict, per sample
     roofline = None
     if phases is not None:
         dom = max(phases, key=phases.get)
-        # algorithmic bytes per launch (DESIGN.md "Algorithmic bytes")
         nu = len(torch.unique(bu[sl(W)])); ni = len(torch.unique(bi[sl(W)]))
-        alg = {
-            "train_step_grads": (4 * R + 24) * B,              # row gather + indices + label
+        # algorithmic bytes per launch
+        alg_bytes = {
+            "train_step_grads": (4 * R + 24) * B,              # row gather + indices + label/logit
             "adam_step": 6 * 4 * (f + d) * (nu + ni),          # p, m, v read + write on touched rows
             "adam_prepare": 16 * B + 6 * 4 * (f + d) * (nu + ni),
-        }[dom]
-        achieved = alg / (phases[dom] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg, "launch_ms": phases[dom],
-                    "phase_ms": phases,
-                    "step_level": {"bytes_per_sample": 4 * R * 7 + 24,
-                                   "achieved": (4 * R * 7 + 24) * value / 1e9,
-                                   "frac": (4 * R * 7 + 24) * value / 1e9 / peak}}
+        }
+        hbm = {n: {"algorithmic_bytes": alg_bytes[n], "ms": phases[n],
+                   "achieved_gbs": alg_bytes[n] / (phases[n] * 1e-3) / 1e9,
+                   "frac": alg_bytes[n] / (phases[n] * 1e-3) / 1e9 / hbm_peak} for n in phases}
+        traffic = profile_traffic(dom)
+        if dom == "train_step_grads" and f >= 32:
+            # the fused fwd+bwd kernel is bound by the tensor pipe in fp32-parity (3xTF32) mode:
+            # algorithmic FLOPs = 6 * MACs per sample (forward 2, dgrad 2, wgrad 2)
+            flops = 6.0 * macs * B
+            achieved = flops / (phases[dom] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "ncf_mma_tile_kernel (ncf_train_step_grads)",
+                        "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tensor_peak, "traffic": traffic,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); the kernel runs fp32-parity "
+                                       "3xTF32 on mma.sync, i.e. 3 TF32 MMAs per algorithmic MAC",
+                        "algorithmic_flops_per_launch": flops, "launch_ms": phases[dom]}
+        else:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": hbm[dom]["achieved_gbs"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": hbm[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes[dom], "launch_ms": phases[dom]}
+        roofline["phase_ms"] = phases
+        roofline["hbm_view"] = hbm
+        roofline["hbm_peak_gbs"] = hbm_peak
+        roofline["step_level"] = {"bytes_per_sample": 4 * R * 7 + 24,
+                                  "achieved_gbs": (4 * R * 7 + 24) * value / 1e9,
+                                  "frac": (4 * R * 7 + 24) * value / 1e9 / hbm_peak}
+
+    # ---- evaluation throughput (second half of the metric: eval users/s) -----------------------------------
+    eval_info = None
+    if world == 1:
+        from ncf_b200.metrics import evaluate
+        ts.flush()
+        model.eval()
+        n_users = inter.test_users.numel()
+        with torch.no_grad():
+            evaluate(model, inter.test_users, inter.test_cands, 10)
+            torch.cuda.synchronize()
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            for _ in range(3):
+                res = evaluate(model, inter.test_users, inter.test_cands, 10)
+            ee1.record()
+            torch.cuda.synchronize()
+        ev_ms = ee0.elapsed_time(ee1) / 3
+        eval_info = {"users_per_s": n_users / (ev_ms * 1e-3), "ms": ev_ms, "users": n_users, "candidates": 100,
+                     "hr10": float(res.hit.float().mean().item())}
 
     # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only) ---------------------------
     cpu_baseline = None
@@ -329,7 +385,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "final_loss": float(host_loss[0]),
+        "eval": eval_info,
+        "tower_math": args.tower_math,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -351,6 +408,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="ml20m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tower-math", choices=["fp32", "tf32"], default="fp32",
+                    help="fp32 = 3xTF32 parity mode (headline); tf32 = single-pass opt-in mode")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

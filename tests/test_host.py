@@ -190,3 +190,14 @@ def test_replicated_dp_plan_gloo_world2():
     out = mgr.dict()
     mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """`from src.ncf.models import NCF` etc. (the reference's import paths) work unchanged."""
+    from src.data.datasets import NCFData, load_all  # noqa: F401
+    from src.distillation import ResponseDistillation
+    from src.ncf.models import NCF
+    from src.training.metrics import metrics
+    from src.utils.config import config
+    assert NCF.__module__ == "ncf_b200.models" and metrics.__module__ == "ncf_b200.metrics"
+    assert ResponseDistillation.__module__ == "ncf_b200.distillation" and config.batch_size == 256
