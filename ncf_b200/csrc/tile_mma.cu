@@ -230,8 +230,13 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
 
   // 3-deep ring, one barrier per chunk: the barrier that publishes chunk c also certifies that
   // every warp is done with chunk c-1, whose buffer the load of chunk c+2 then overwrites.
-  load_chunk(0, stage);
-  if (nchunks > 1) load_chunk(1, stage + kStageFloats);
+  // Every CTA walks the contraction in a different rotation (chunk c + rot): the sum does not care
+  // about the order, and it keeps the 148 CTAs from asking L2 for the same weight lines at the
+  // same moment (measured: the un-rotated walk is bound by the latency of that hot spot).
+  const int rot = (int)(blockIdx.x % (unsigned)nchunks);
+  auto logical = [&](int c) { const int cc = c + rot; return cc >= nchunks ? cc - nchunks : cc; };
+  load_chunk(logical(0), stage);
+  if (nchunks > 1) load_chunk(logical(1), stage + kStageFloats);
   int slot = 0;
   for (int c = 0; c < nchunks; ++c) {
     const uint32_t b_addr = b_sh0 + slot * (kStageFloats * 4);
@@ -239,13 +244,14 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
     __syncthreads();
     if (c + 2 < nchunks) {
       const int s2 = slot + 2 >= kStages ? slot + 2 - kStages : slot + 2;
-      load_chunk(c + 2, stage + s2 * kStageFloats);
+      load_chunk(logical(c + 2), stage + s2 * kStageFloats);
     }
     slot = slot + 1 == kStages ? 0 : slot + 1;
     if (active) {
-      const uint32_t a_addr = a_sh + c * 64;  // 2 k-steps x 8 floats
+      const int cc = logical(c);
+      const uint32_t a_addr = a_sh + cc * 64;  // 2 k-steps x 8 floats
       k_step(a_addr, b_addr);
-      if (c * 2 + 1 < nks) k_step(a_addr + 32, b_addr + 64);
+      if (cc * 2 + 1 < nks) k_step(a_addr + 32, b_addr + 64);
     }
   }
   __syncthreads();  // stage buffers are free again; also orders the epilogue after all A reads

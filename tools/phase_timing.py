@@ -8,6 +8,8 @@ lib = _lib.load()
 dev = torch.device("cuda:0")
 U, I, f, L, B = 138493, 26744, 32, 3, 65536
 model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
+model.tower_math = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+print("tower_math", model.tower_math)
 ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
 g = torch.Generator(device=dev).manual_seed(0)
 u = torch.randint(0, U, (B,), device=dev, generator=g); i = torch.randint(0, I, (B,), device=dev, generator=g)
