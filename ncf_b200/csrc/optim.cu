@@ -106,59 +106,9 @@ struct RowsParams {
   AdamConst c;
 };
 
-// One warp brings the combined row (GMF part of f floats, then MLP part of d floats) of one table
-// side up to date.  16-byte chunks are dealt to the lanes; every load of the row (g, p, m, v of both
-// tables) is issued before anything is computed, so a row costs one DRAM round trip.
-template <bool REAL_STEP>
-__device__ __forceinline__ void adam_combined_row_vec(const RowsParams& q, int side, int64_t r,
-                                                      int gap, const float* c1s, const float* c2s,
-                                                      float c1t, float c2t, int lane) {
-  constexpr int kMaxIter = 3;  // (f + d) / 4 <= 96 chunks
-  const int cf = q.has_gmf ? q.f >> 2 : 0, cd = q.has_mlp ? q.d >> 2 : 0;
-  const int chunks = cf + cd;
-  float4 p4[kMaxIter], m4[kMaxIter], v4[kMaxIter], g4[kMaxIter];
-  float *P[kMaxIter], *M[kMaxIter], *Vv[kMaxIter], *G[kMaxIter];
-#pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int ch = lane + 32 * it;
-    if (ch < chunks) {
-      const bool gm = ch < cf;
-      const int64_t o = gm ? r * q.f + 4 * ch : r * q.d + 4 * (ch - cf);
-      P[it] = (gm ? q.p_gmf[side] : q.p_mlp[side]) + o;
-      M[it] = (gm ? q.m_gmf[side] : q.m_mlp[side]) + o;
-      Vv[it] = (gm ? q.v_gmf[side] : q.v_mlp[side]) + o;
-      p4[it] = *reinterpret_cast<const float4*>(P[it]);
-      m4[it] = *reinterpret_cast<const float4*>(M[it]);
-      v4[it] = *reinterpret_cast<const float4*>(Vv[it]);
-      if (REAL_STEP) {
-        G[it] = (gm ? q.g_gmf[side] : q.g_mlp[side]) + o;
-        g4[it] = *reinterpret_cast<const float4*>(G[it]);
-      }
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int ch = lane + 32 * it;
-    if (ch < chunks) {
-      float* pp = &p4[it].x; float* mp = &m4[it].x; float* vp = &v4[it].x; float* gp = &g4[it].x;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        replay_zero_steps(pp[k], mp[k], vp[k], gap, c1s, c2s, q.c);
-        if (REAL_STEP) adam_real_step(pp[k], mp[k], vp[k], gp[k], c1t, c2t, q.c);
-      }
-      *reinterpret_cast<float4*>(P[it]) = p4[it];
-      *reinterpret_cast<float4*>(M[it]) = m4[it];
-      *reinterpret_cast<float4*>(Vv[it]) = v4[it];
-      if (REAL_STEP) *reinterpret_cast<float4*>(G[it]) = make_float4(0, 0, 0, 0);
-    }
-  }
-}
-
 // mode 0: Adam step on the touched rows; mode 1: flush (all rows, replay only);
 // mode 2: catch-up (touched rows, replay only) — run BEFORE the forward of a step so that the rows
 // the batch is about to read are at the dense-Adam state of the previous step.
-// Each warp takes 32 list entries at a time: the lanes fetch (row id, last_step) in parallel, then
-// the warp walks the rows that need work — so the metadata latency is paid once per 32 rows.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q) {
   __shared__ float c1_sm[kWarps][kMaxReplay];
@@ -169,64 +119,45 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
   const int64_t step_now = *q.step;
   const int64_t t = (MODE == 0) ? step_now + 1 : step_now;  // state is brought to "after step t"
   const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
-  const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0) && (q.f + q.d) <= 384;
+  const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
   int64_t n0, n1;
   if (MODE != 1) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
   const int64_t total = n0 + n1;
   const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
-  for (int64_t base = wid * 32; base < total; base += nw * 32) {
-    const int64_t e = base + lane;
-    int my_side = 0, my_gap = 0;
-    int32_t my_last = 0;
-    int64_t my_r = 0;
-    bool need = false;
-    if (e < total) {
-      my_side = e < n0 ? 0 : 1;
-      const int64_t k = my_side ? e - n0 : e;
-      my_r = (MODE != 1) ? q.list[my_side][k] : k;
-      my_last = q.last[my_side][my_r];
-      if (MODE == 0) {
-        my_gap = (my_last > 0) ? (int)(t - 1 - my_last) : 0;
-        need = true;
-      } else {
-        need = my_last > 0 && my_last < t;
-        my_gap = (int)(t - my_last);
-      }
+  for (int64_t e = wid; e < total; e += nw) {
+    const int side = e < n0 ? 0 : 1;
+    const int64_t r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+    const int32_t last = q.last[side][r];
+    int gap;
+    if (MODE == 0) {
+      gap = (last > 0) ? (int)(t - 1 - last) : 0;
+    } else {
+      if (last <= 0 || last >= t) continue;
+      gap = (int)(t - last);
     }
-    unsigned todo = __ballot_sync(0xffffffffu, need);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int side = __shfl_sync(0xffffffffu, my_side, src);
-      const int gap = __shfl_sync(0xffffffffu, my_gap, src);
-      const int32_t last = __shfl_sync(0xffffffffu, my_last, src);
-      const int64_t r = __shfl_sync(0xffffffffu, my_r, src);
-      __syncwarp();
-      const int n = min(gap, kMaxReplay);
-      for (int j = lane; j < n; j += 32) {
-        const float s = (float)(last + 1 + j);
-        c1s[j] = bias_c1(q.c, s);
-        c2s[j] = bias_c2(q.c, s);
-      }
-      __syncwarp();
-      if (vec) {
-        adam_combined_row_vec<MODE == 0>(q, side, r, gap, c1s, c2s, c1t, c2t, lane);
-      } else {
-        if (q.has_gmf) {
-          const int64_t o = r * q.f;
-          adam_row<1>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o,
-                      (MODE == 0) ? q.g_gmf[side] + o : nullptr, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
-        }
-        if (q.has_mlp) {
-          const int64_t o = r * q.d;
-          adam_row<1>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o,
-                      (MODE == 0) ? q.g_mlp[side] + o : nullptr, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
-        }
-      }
-      if (lane == 0) {
-        q.last[side][r] = (int32_t)t;
-        if (MODE == 0) q.flag[side][r] = 0;
-      }
+    __syncwarp();
+    const int n = min(gap, kMaxReplay);
+    for (int j = lane; j < n; j += 32) {
+      const float s = (float)(last + 1 + j);
+      c1s[j] = bias_c1(q.c, s);
+      c2s[j] = bias_c2(q.c, s);
+    }
+    __syncwarp();
+    if (q.has_gmf) {
+      const int64_t o = r * q.f;
+      float* G = (MODE == 0) ? q.g_gmf[side] + o : nullptr;
+      if (vec) adam_row<4>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
+      else adam_row<1>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
+    }
+    if (q.has_mlp) {
+      const int64_t o = r * q.d;
+      float* G = (MODE == 0) ? q.g_mlp[side] + o : nullptr;
+      if (vec) adam_row<4>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
+      else adam_row<1>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
+    }
+    if (lane == 0) {
+      q.last[side][r] = (int32_t)t;
+      if (MODE == 0) q.flag[side][r] = 0;
     }
   }
 }

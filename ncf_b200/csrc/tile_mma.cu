@@ -230,11 +230,9 @@ __device__ __forceinline__ void gemm_act_weight(const float* __restrict__ A, int
 
   // 3-deep ring, one barrier per chunk: the barrier that publishes chunk c also certifies that
   // every warp is done with chunk c-1, whose buffer the load of chunk c+2 then overwrites.
-  // Every CTA walks the contraction in a different rotation (chunk c + rot): the sum does not care
-  // about the order, and it keeps the 148 CTAs from asking L2 for the same weight lines at the
-  // same moment (measured: the un-rotated walk is bound by the latency of that hot spot).
-  const int rot = (int)(blockIdx.x % (unsigned)nchunks);
-  auto logical = [&](int c) { const int cc = c + rot; return cc >= nchunks ? cc - nchunks : cc; };
+  // (Rotating the chunk order per CTA to de-synchronise the L2 requests of the 148 CTAs was
+  // measured and makes no difference — profiles/ablation_r01.md — so the walk is in order.)
+  auto logical = [&](int c) { return c; };
   load_chunk(logical(0), stage);
   if (nchunks > 1) load_chunk(logical(1), stage + kStageFloats);
   int slot = 0;
