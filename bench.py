@@ -386,11 +386,54 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "eval": eval_info,
+        "small_config": small_config_run(dev) if (world == 1 and args.workload == "ml20m") else None,
         "tower_math": args.tower_math,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_config_run(dev, epochs_steps: int = 2048):
+    """BASELINE configs[1] for reference: NeuMF f=8 L=3 on the synthetic ML-1M shape at the
+    reference batch 256 — launch-latency-bound, so it runs as CUDA-graph windows of
+    64 steps through the same public API (EpochStream + FusedTrainStep + train_epoch machinery):
+    on-device negative sampling, shuffle, fused steps, no host sync.  Reported beside the headline."""
+    import torch
+    from ncf_b200.models import NCF
+    from ncf_b200.synth import make_interactions
+    from ncf_b200.trainer import EpochStream, FusedTrainStep
+    inter = make_interactions("ml1m", device=dev)
+    torch.manual_seed(0)
+    model = NCF(inter.user_num, inter.item_num, 8, 3, 0.0, "NeuMF-end").to(dev)
+    B, W = 256, 64
+    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    stream = EpochStream(inter.pos_user, inter.pos_item, inter.user_num, inter.item_num, num_ng=4, seed=1)
+    t_s0 = time.perf_counter()
+    stream.begin_epoch(0)
+    torch.cuda.synchronize()
+    sample_ms = (time.perf_counter() - t_s0) * 1e3
+    wu = torch.empty(W * B, dtype=torch.int64, device=dev)
+    wi = torch.empty(W * B, dtype=torch.int64, device=dev)
+    wl = torch.empty(W * B, dtype=torch.float32, device=dev)
+    stream.fill(0, W * B, wu, wi, wl)
+    for k in range(W):  # eager warm-up window (loads every kernel before capture)
+        ts.step(wu[k * B:(k + 1) * B], wi[k * B:(k + 1) * B], wl[k * B:(k + 1) * B])
+    graph = ts.capture(wu, wi, wl, B)
+    n_windows = max(1, epochs_steps // W)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for w in range(n_windows):
+        stream.fill((w + 1) * W * B, W * B, wu, wi, wl)
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps = n_windows * W
+    return {"workload": "NeuMF f=8 L=3, synthetic ml1m shape, batch 256, Adam, CUDA-graph windows of 64 steps",
+            "samples_per_s": steps * B / (ms * 1e-3), "us_per_step": ms * 1e3 / steps, "steps": steps,
+            "ng_sample_ms_per_epoch": sample_ms, "negatives_per_epoch": int(stream.P * 4)}
 
 
 def make_dp_sync(ts, world):

@@ -170,6 +170,14 @@ int ncf_train_step_grads(const NcfModel* m_host, const NcfGrads* g_host, const i
                          float alpha, int64_t B, double* loss_accum, float* logits_out,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same as ncf_train_step_grads, but the loss mean (and hence dloss/dlogit) is taken over B_norm >= B
+ * samples: the B local samples of this rank are a slice of a global batch of B_norm (multi-GPU). */
+int ncf_train_step_grads_norm(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* user,
+                              const int64_t* item, const float* label, const float* teacher_logits,
+                              float alpha, int64_t B, int64_t B_norm, double* loss_accum,
+                              float* logits_out, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+
 /* ---- a9 alone: backward from a caller-supplied dloss/dlogit ---------------------------------------
  * Replaces autograd's backward through NCF.forward (reference scripts/train_neumf.py:114) when the
  * loss was computed elsewhere (e.g. by torch in an unmodified reference loop): recomputes the
@@ -189,6 +197,13 @@ int ncf_backward(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* 
  * (Adam; it marks and catches up) or ncf_mark_rows (SGD) on the same batch. */
 int ncf_mark_rows(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* user,
                   const int64_t* item, int64_t B, void* stream);
+/* One side at a time (side 0 = users, 1 = items), for row lists that do not pair up: row-sharded
+ * tables register a rank's own users and the item rows other ranks requested separately. */
+int ncf_mark_rows_side(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* rows, int64_t n,
+                       int32_t side, void* stream);
+/* Replays the pending zero-gradient Adam steps of every row currently in g's touched lists. */
+int ncf_adam_catchup(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
+                     NcfAdamHyper h, void* stream);
 /* ncf_adam_prepare: call BEFORE ncf_train_step_grads of the same batch.  Registers the batch's
  * distinct rows in g's touched lists and replays their pending zero-gradient steps, so that the
  * forward reads the rows exactly as the reference's dense Adam would have left them. */
@@ -200,6 +215,22 @@ int ncf_adam_step(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamS
 int ncf_adam_flush(const NcfModel* m_host, const NcfAdamState* s_host, NcfAdamHyper h,
                    void* stream);
 int ncf_sgd_step(const NcfModel* m_host, const NcfGrads* g_host, float lr, void* stream);
+
+/* ---- (e) row-sharded tables: pack / unpack around the NCCL all-to-alls ----------------------------------
+ * New design (the reference is single-process).  Row r lives on rank r % world at
+ * local index r / world.
+ * ncf_bucket_by_owner: groups the n samples by the owner of their item: perm[pos] = sample index,
+ *   local_idx[pos] = item / world, counts[w] = samples whose item lives on rank w; cursor is
+ *   int32[world] scratch.  ncf_permute_*: out[i] = in[perm[i]].
+ * ncf_gather_rows: out[i][:] = table[idx[i]][:].  ncf_scatter_add_rows: table[idx[i]][:] += in[i][:]. */
+int ncf_bucket_by_owner(const int64_t* item, int64_t n, int32_t world, int64_t* perm,
+                        int64_t* local_idx, int32_t* counts, int32_t* cursor, void* stream);
+int ncf_permute_i64(const int64_t* in, const int64_t* perm, int64_t n, int64_t* out, void* stream);
+int ncf_permute_f32(const float* in, const int64_t* perm, int64_t n, float* out, void* stream);
+int ncf_gather_rows(const float* table, const int64_t* idx, int64_t n, int32_t dim, int64_t rows,
+                    float* out, void* stream);
+int ncf_scatter_add_rows(float* table, const int64_t* idx, int64_t n, int32_t dim, int64_t rows,
+                         const float* in, void* stream);
 
 /* ---- a11: leave-one-out evaluation --------------------------------------------------------------
  * Replaces metrics() (reference src/training/metrics.py:4-25).  scores is [n, C]; column 0 is the

@@ -65,6 +65,14 @@ SIGNATURES = {
     "ncf_loss_grad": (C.c_int, [_vp, _vp, _vp, _fl, _i64, _vp, _vp, _vp]),
     "ncf_train_workspace_bytes": (_i64, [_P(NcfModel), _i64]),
     "ncf_train_step_grads": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _vp, _fl, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ncf_train_step_grads_norm": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _vp, _fl, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "ncf_mark_rows_side": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _i64, _i32, _vp]),
+    "ncf_adam_catchup": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
+    "ncf_bucket_by_owner": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ncf_permute_i64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "ncf_permute_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "ncf_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "ncf_scatter_add_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "ncf_backward": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "ncf_mark_rows": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _i64, _vp]),
     "ncf_adam_prepare": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp, _vp, _i64, _vp]),

@@ -234,6 +234,18 @@ __global__ void mark_rows_kernel(const int64_t* __restrict__ user, const int64_t
   }
 }
 
+// One side only (users or items): rows[] need not pair up with anything (row-sharded tables: a
+// rank registers its own users and, separately, the item rows other ranks asked it for).
+__global__ void mark_side_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t limit,
+                                 int32_t* flag, int64_t* list, int32_t* count) {
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n;
+       b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = rows[b];
+    if (r < 0 || r >= limit) continue;
+    if (atomicExch(&flag[r], 1) == 0) list[atomicAdd(count, 1)] = r;
+  }
+}
+
 __global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
   if (step) *step += 1;
   tcount[0] = 0;
@@ -352,6 +364,38 @@ extern "C" int ncf_mark_rows(const NcfModel* m, const NcfGrads* g, const int64_t
   if ((rc = check_grads(m, g)) != NCF_OK) return rc;
   NCF_REQUIRE(B > 0 && user && item, "ncf_mark_rows: empty batch or null pointer");
   return launch_mark(m, g, user, item, B, (cudaStream_t)stream);
+}
+
+extern "C" int ncf_mark_rows_side(const NcfModel* m, const NcfGrads* g, const int64_t* rows, int64_t n,
+                                  int32_t side, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  NCF_REQUIRE(side == 0 || side == 1, "ncf_mark_rows_side: side must be 0 (users) or 1 (items)");
+  NCF_REQUIRE(n >= 0, "ncf_mark_rows_side: negative n");
+  if (n == 0) return NCF_OK;
+  NCF_REQUIRE(rows != nullptr, "ncf_mark_rows_side: rows is NULL");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4 * ncf::num_sms()) blocks = 4 * ncf::num_sms();
+  mark_side_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      rows, n, side ? m->item_num : m->user_num, side ? g->item_flag : g->user_flag,
+      side ? g->item_list : g->user_list, g->touched_count + side);
+  NCF_LAUNCH_CHECK("mark_side_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_adam_catchup(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
+                                NcfAdamHyper h, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  if ((rc = check_state(m, s)) != NCF_OK) return rc;
+  RowsParams q{};
+  fill_rows(q, m, g, s);
+  q.c = make_const(h);
+  adam_rows_kernel<2><<<ncf::num_sms() * 8, kThreads, 0, (cudaStream_t)stream>>>(q);
+  NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
+  return NCF_OK;
 }
 
 extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,

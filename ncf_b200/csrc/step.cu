@@ -116,7 +116,8 @@ extern "C" int64_t ncf_train_workspace_bytes(const NcfModel* m, int64_t B) {
 static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* user,
                         const int64_t* item, const float* label, const float* teacher_logits,
                         const float* dlogit_in, float alpha, int64_t B, double* loss_accum,
-                        float* logits_out, void* workspace, int64_t workspace_bytes, void* stream);
+                        float* logits_out, void* workspace, int64_t workspace_bytes, void* stream,
+                        int64_t B_norm = 0);
 
 extern "C" int ncf_backward(const NcfModel* m, const NcfGrads* g, const int64_t* user,
                             const int64_t* item, const float* dlogit, int64_t B, void* workspace,
@@ -136,10 +137,22 @@ extern "C" int ncf_train_step_grads(const NcfModel* m, const NcfGrads* g, const 
                       logits_out, workspace, workspace_bytes, stream);
 }
 
+extern "C" int ncf_train_step_grads_norm(const NcfModel* m, const NcfGrads* g, const int64_t* user,
+                                         const int64_t* item, const float* label,
+                                         const float* teacher_logits, float alpha, int64_t B,
+                                         int64_t B_norm, double* loss_accum, float* logits_out,
+                                         void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(label && loss_accum, "ncf_train_step_grads_norm: null pointer");
+  NCF_REQUIRE(B_norm >= B, "ncf_train_step_grads_norm: B_norm must be >= B");
+  return train_common(m, g, user, item, label, teacher_logits, nullptr, alpha, B, loss_accum,
+                      logits_out, workspace, workspace_bytes, stream, B_norm);
+}
+
 static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* user,
                         const int64_t* item, const float* label, const float* teacher_logits,
                         const float* dlogit_in, float alpha, int64_t B, double* loss_accum,
-                        float* logits_out, void* workspace, int64_t workspace_bytes, void* stream) {
+                        float* logits_out, void* workspace, int64_t workspace_bytes, void* stream,
+                        int64_t B_norm) {
   int rc = ncf::validate_model(m);
   if (rc != NCF_OK) return rc;
   NCF_REQUIRE(B > 0, "ncf_train_step_grads: empty batch");
@@ -167,7 +180,7 @@ static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* use
   p.dlogit_in = dlogit_in;
   p.alpha = teacher_logits ? alpha : 1.f;
   p.B = B;
-  p.invB = 1.f / (float)B;
+  p.invB = 1.f / (float)(B_norm > 0 ? B_norm : B);  // mean over the (global) batch
   p.logits = logits_out;
   p.loss_accum = loss_accum;
   if (ncf::mma_tile_rows(p) != 0) {

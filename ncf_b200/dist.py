@@ -96,3 +96,138 @@ class ReplicatedDataParallel:
             worst = torch.maximum(worst, (p.data - ref).abs().max().reshape(1))
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         return float(worst.item())
+
+
+# ---- row-sharded tables (BASELINE config 5) ------------------------------------------------------------------
+def shard_rows(n_rows: int, world: int, rank: int) -> int:
+    """Number of rows r in [0, n_rows) with r % world == rank."""
+    return (n_rows - rank + world - 1) // world
+
+
+def shard_state_dict(full: dict, world: int, rank: int) -> dict:
+    """The slice of a full-model state_dict that lives on `rank`: table row r -> rank r % world, local
+    index r // world; the tower is replicated."""
+    out = {}
+    for k, v in full.items():
+        out[k] = v[rank::world].clone() if k.startswith("embed_") else v.clone()
+    return out
+
+
+class RowShardedTrainer:
+    """Training with the four embedding tables (and their Adam state) row-sharded over the ranks.
+
+    Each rank trains on samples of ITS OWN users (sharding follows the data), so user rows are
+    local and only item rows travel.  Per step (all NCCL, one process per GPU):
+      1. bucket the local samples by item owner (ncf_bucket_by_owner) and all-to-all the counts;
+      2. all-to-all #1: requested item indices -> owners; owners register them and their own users,
+         replay pending Adam steps (dense-equivalence), gather the rows;
+      3. all-to-all #2: item rows (GMF f + MLP d floats per sample) back to the requesters;
+      4. fused forward+loss+backward on [local user tables | received item rows], the loss mean
+         taken over the GLOBAL batch (ncf_train_step_grads_norm);
+      5. all-to-all #3: per-sample item-row gradients -> owners, scatter-added into their shard;
+      6. all-reduce (sum) of the tower gradients; sparse-row Adam on every rank's shard.
+    The result equals single-process training at the global batch (tests/shard_worker.py).
+    Split sizes come back to the host once per step (one small D2H) — fixed-capacity buckets that
+    avoid it are a refinement."""
+
+    def __init__(self, shard_model, user_num: int, item_num: int, lr: float = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_batch: int = 65536):
+        from .trainer import FusedTrainStep
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.user_num, self.item_num = int(user_num), int(item_num)
+        self.model = shard_model
+        if shard_model.user_num != shard_rows(user_num, self.world, self.rank) or \
+                shard_model.item_num != shard_rows(item_num, self.world, self.rank):
+            raise ValueError("shard_model must hold exactly this rank's rows")
+        # the shard's optimiser state, gradient buffers and lists (items: up to world * max_batch requests)
+        self.ts = FusedTrainStep(shard_model, "adam", lr, betas, eps, max_batch=max_batch)
+        dev = self.ts.device
+        self.ts.grads.item_list = torch.zeros(min(max_batch * self.world, shard_model.item_num),
+                                              dtype=torch.int64, device=dev)
+        self.ts._refresh()
+        self.max_batch = max_batch
+        self.f, self.d = shard_model.factor_num, shard_model.factor_num << (shard_model.num_layers - 1)
+        self.loss_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        for name in ("MLP_layers", "predict_layer"):  # identical tower everywhere
+            for p in getattr(shard_model, name).parameters():
+                dist.broadcast(p.data, src=0)
+
+    def _a2a(self, send: torch.Tensor, send_counts, recv_counts, row: int = 1) -> torch.Tensor:
+        out = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(out, send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts))
+        return out
+
+    def step(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor) -> None:
+        """user: GLOBAL ids owned by this rank; item: GLOBAL ids; label: float32."""
+        ts, W, dev = self.ts, self.world, self.ts.device
+        b = user.numel()
+        # global batch size (for the loss mean) and the item-owner buckets
+        perm, local_item, counts = ops.bucket_by_owner(item, W)
+        meta = torch.cat([counts.to(torch.int64), torch.tensor([b], dtype=torch.int64, device=dev)])
+        all_meta = torch.empty(W, W + 1, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_meta.view(-1), meta)
+        all_meta = all_meta.cpu()                                # the one host sync of the step
+        send_counts = all_meta[self.rank, :W].tolist()            # my samples per owner
+        recv_counts = all_meta[:, self.rank].tolist()             # requests I receive per rank
+        B_global = int(all_meta[:, W].sum())
+        # 1-2. ask the owners
+        req = self._a2a(local_item, send_counts, recv_counts)     # local item indices requested from me
+        local_user = (user // W).contiguous()
+        ops.mark_rows_side(ts._m, ts._g, local_user, 0)
+        ops.mark_rows_side(ts._m, ts._g, req, 1)
+        ops.adam_catchup(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
+        m = self.model
+        rows_gmf = ops.gather_rows(m.embed_item_GMF.weight.detach(), req)
+        rows_mlp = ops.gather_rows(m.embed_item_MLP.weight.detach(), req)
+        # 3. rows come back in my bucket order
+        got_gmf = self._a2a(rows_gmf, recv_counts, send_counts)
+        got_mlp = self._a2a(rows_mlp, recv_counts, send_counts)
+        # 4. fused step on [my user shard | received item rows]
+        u_sorted = ops.permute(local_user, perm)
+        y_sorted = ops.permute(label, perm)
+        item_pos = torch.arange(b, dtype=torch.int64, device=dev)
+        g_gmf = torch.zeros_like(got_gmf)
+        g_mlp = torch.zeros_like(got_mlp)
+        cm = ops.model_struct(m.abi_type(), m.factor_num, m.num_layers, m.user_num, b,
+                              (m.embed_user_GMF.weight.detach(), got_gmf, m.embed_user_MLP.weight.detach(), got_mlp),
+                              [(l.weight.detach(), l.bias.detach()) for l in m.linears()],
+                              (m.predict_layer.weight.detach(), m.predict_layer.bias.detach()),
+                              tower_math=m.tower_math)
+        cg = ts.grads.struct()
+        cg.g_item_gmf, cg.g_item_mlp = ops.ptr(g_gmf), ops.ptr(g_mlp)
+        ops.train_step_grads_norm(cm, cg, u_sorted, item_pos, y_sorted, B_global, self.loss_accum, ts.workspace)
+        # 5. item-row gradients go home
+        back_gmf = self._a2a(g_gmf, send_counts, recv_counts)
+        back_mlp = self._a2a(g_mlp, send_counts, recv_counts)
+        ops.scatter_add_rows(ts.grads.g_item_gmf, req, back_gmf)
+        ops.scatter_add_rows(ts.grads.g_item_mlp, req, back_mlp)
+        # 6. tower gradients: every rank holds (local sum) / B_global -> sum over ranks
+        dist.all_reduce(ts.grads.g_tower, op=dist.ReduceOp.SUM)
+        ops.adam_step(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
+        ts._dirty = True
+        ts.num_steps += 1
+
+    def flush(self):
+        self.ts.flush()
+
+    def gather_full_state(self) -> dict:
+        """Reassembles the full-model state_dict on every rank (tests / checkpoints)."""
+        self.flush()
+        out = {}
+        for k, v in self.model.state_dict().items():
+            if not k.startswith("embed_"):
+                out[k] = v.clone()
+                continue
+            n_rows = self.user_num if "user" in k else self.item_num
+            per = shard_rows(n_rows, self.world, 0)
+            pad = torch.zeros(per, v.shape[1], dtype=v.dtype, device=v.device)
+            pad[: v.shape[0]] = v
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad)
+            full = torch.empty(n_rows, v.shape[1], dtype=v.dtype, device=v.device)
+            for r in range(self.world):
+                full[r::self.world] = parts[r][: shard_rows(n_rows, self.world, r)]
+            out[k] = full
+        return out

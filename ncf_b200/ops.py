@@ -335,3 +335,60 @@ def eval_users(m: NcfModel, users: torch.Tensor, cands: torch.Tensor, k: int):
                              k, ptr(hit), ptr(rank), ptr(ndcg), ptr(topk), ptr(scores), ptr(ws),
                              ws_bytes, current_stream()), "ncf_eval_users")
     return hit, rank, ndcg, topk, scores
+
+
+# ---- (e) row-sharded tables -------------------------------------------------------------------------------
+def train_step_grads_norm(m: NcfModel, g: NcfGrads, user, item, label, B_norm: int,
+                          loss_accum: torch.Tensor, workspace: torch.Tensor) -> None:
+    """Fused step whose loss mean runs over B_norm >= len(user) samples (a slice of a global batch)."""
+    check(_lib.load().ncf_train_step_grads_norm(
+        C.byref(m), C.byref(g), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+        ptr(_f32(label, "label")), None, 1.0, user.numel(), int(B_norm), ptr(loss_accum), None,
+        ptr(workspace), workspace.numel() * workspace.element_size(), current_stream()),
+        "ncf_train_step_grads_norm")
+
+
+def mark_rows_side(m: NcfModel, g: NcfGrads, rows: torch.Tensor, side: int) -> None:
+    check(_lib.load().ncf_mark_rows_side(C.byref(m), C.byref(g), ptr(_i64(rows, "rows")), rows.numel(),
+                                         side, current_stream()), "ncf_mark_rows_side")
+
+
+def adam_catchup(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().ncf_adam_catchup(C.byref(m), C.byref(g), C.byref(s),
+                                       NcfAdamHyper(lr, beta1, beta2, eps), current_stream()),
+          "ncf_adam_catchup")
+
+
+def bucket_by_owner(item: torch.Tensor, world: int):
+    """-> (perm int64[n], local_idx int64[n], counts int32[world]) with samples grouped by item % world."""
+    n, dev = item.numel(), item.device
+    perm = torch.empty(n, dtype=torch.int64, device=dev)
+    local_idx = torch.empty(n, dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int32, device=dev)
+    cursor = torch.empty(world, dtype=torch.int32, device=dev)
+    check(_lib.load().ncf_bucket_by_owner(ptr(_i64(item, "item")), n, world, ptr(perm), ptr(local_idx),
+                                          ptr(counts), ptr(cursor), current_stream()),
+          "ncf_bucket_by_owner")
+    return perm, local_idx, counts
+
+
+def permute(src: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(src)
+    fn = {torch.int64: "ncf_permute_i64", torch.float32: "ncf_permute_f32"}[src.dtype]
+    check(getattr(_lib.load(), fn)(ptr(src), ptr(_i64(perm, "perm")), src.numel(), ptr(out),
+                                   current_stream()), fn)
+    return out
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(idx.numel(), table.shape[1], dtype=torch.float32, device=table.device)
+    check(_lib.load().ncf_gather_rows(ptr(_f32(table, "table")), ptr(_i64(idx, "idx")), idx.numel(),
+                                      table.shape[1], table.shape[0], ptr(out), current_stream()),
+          "ncf_gather_rows")
+    return out
+
+
+def scatter_add_rows(table: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor) -> None:
+    check(_lib.load().ncf_scatter_add_rows(ptr(_f32(table, "table")), ptr(_i64(idx, "idx")), idx.numel(),
+                                           table.shape[1], table.shape[0], ptr(_f32(rows, "rows")),
+                                           current_stream()), "ncf_scatter_add_rows")

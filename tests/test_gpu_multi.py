@@ -21,3 +21,14 @@ def test_replicated_dp_two_gpus():
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["divergence"] == 0.0          # NCCL all-reduce leaves identical gradients everywhere
     assert res["vs_single_process"] < 2e-4   # same trajectory as one process at the global batch
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_sharded_two_gpus():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", str(ROOT / "tests" / "shard_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["vs_single_process"] < 2e-4
+    assert abs(res["loss_sharded"] - res["loss_single"]) < 1e-5 * abs(res["loss_single"])

@@ -201,3 +201,18 @@ def test_reference_import_paths_resolve_to_this_package():
     from src.utils.config import config
     assert NCF.__module__ == "ncf_b200.models" and metrics.__module__ == "ncf_b200.metrics"
     assert ResponseDistillation.__module__ == "ncf_b200.distillation" and config.batch_size == 256
+
+
+def test_row_shard_layout_helpers():
+    """Row r -> rank r % world at local index r // world; shards tile the table exactly."""
+    from ncf_b200.dist import shard_rows, shard_state_dict
+    assert [shard_rows(10, 4, r) for r in range(4)] == [3, 3, 2, 2]
+    assert sum(shard_rows(301, 8, r) for r in range(8)) == 301
+    full = {"embed_user_GMF.weight": torch.arange(14.0).reshape(7, 2), "predict_layer.bias": torch.ones(1)}
+    parts = [shard_state_dict(full, 3, r) for r in range(3)]
+    assert parts[1]["embed_user_GMF.weight"][:, 0].tolist() == [2.0, 8.0]      # rows 1 and 4
+    assert all(torch.equal(p["predict_layer.bias"], full["predict_layer.bias"]) for p in parts)
+    rebuilt = torch.empty(7, 2)
+    for r in range(3):
+        rebuilt[r::3] = parts[r]["embed_user_GMF.weight"]
+    assert torch.equal(rebuilt, full["embed_user_GMF.weight"])
