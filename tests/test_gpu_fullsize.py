@@ -1,0 +1,146 @@
+"""Properties at BASELINE.json's full sizes (the oracle is too slow there): the synthetic ML-20M
+shape — 138 493 users x 26 744 items, ~20M interactions, batch 65 536 — checked through
+size-independent invariants, plus the reference-style call paths (`NCFData.ng_sample`,
+`metrics(model, DataLoader, k)`) on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ml20m():
+    from ncf_b200.synth import make_interactions
+    return make_interactions("ml20m", device=dev())
+
+
+def test_sampler_and_shuffle_invariants_at_ml20m(ml20m):
+    from ncf_b200.trainer import EpochStream
+    d = ml20m
+    st = EpochStream(d.pos_user, d.pos_item, d.user_num, d.item_num, num_ng=4, seed=7)
+    # CSR: row pointers are monotone, every row sorted, every positive present
+    assert int(st.rowptr[-1]) == st.P and bool((st.rowptr[1:] >= st.rowptr[:-1]).all())
+    rows = torch.repeat_interleave(torch.arange(d.user_num, device=dev()), st.rowptr[1:] - st.rowptr[:-1])
+    key = rows * d.item_num + st.col.long()
+    assert bool((key[1:] > key[:-1]).all())                     # sorted, no duplicates (synthetic pairs are unique)
+    pos_key = torch.sort(d.pos_user * d.item_num + d.pos_item).values
+    assert torch.equal(pos_key, key)
+    # negatives: in range, never an observed pair, reproducible, different per epoch
+    st.begin_epoch(0)
+    neg0 = st.neg_item.clone()
+    assert int(neg0.min()) >= 0 and int(neg0.max()) < d.item_num
+    nk = torch.repeat_interleave(d.pos_user, 4) * d.item_num + neg0
+    hit = torch.searchsorted(key, nk).clamp_max(key.numel() - 1)
+    assert not bool((key[hit] == nk).any())
+    st.begin_epoch(0)
+    assert torch.equal(neg0, st.neg_item)
+    st.begin_epoch(1)
+    assert float((neg0 != st.neg_item).float().mean()) > 0.99
+    # uniformity over the free items: item histogram of the negatives is flat up to the per-user exclusions
+    hist = torch.bincount(neg0, minlength=d.item_num).float()
+    assert float(hist.std() / hist.mean()) < 0.2
+    # epoch stream: a window is a slice of a permutation of positives-then-negatives
+    S = st.S
+    n = 1 << 22
+    wu = torch.empty(n, dtype=torch.int64, device=dev())
+    wi = torch.empty(n, dtype=torch.int64, device=dev())
+    wl = torch.empty(n, dtype=torch.float32, device=dev())
+    st.fill(S - n, n, wu, wi, wl)                                # the last window of the epoch
+    frac_pos = float(wl.mean())
+    assert abs(frac_pos - 0.2) < 0.01                            # 1 positive per 4 negatives, well mixed
+    pk = wu[wl > 0.5] * d.item_num + wi[wl > 0.5]
+    assert bool((key[torch.searchsorted(key, pk).clamp_max(key.numel() - 1)] == pk).all())  # positives are observed pairs
+
+
+def test_training_step_invariants_at_full_batch(ml20m):
+    """One optimisation step at B = 65 536 on the bench config: gradient buffers are left zero, every
+    touched row moved by about lr, untouched rows did not move, the loss is ~log 2 at init, and a
+    second flush is a no-op (idempotence)."""
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import EpochStream, FusedTrainStep
+    d = ml20m
+    B = 65536
+    torch.manual_seed(0)
+    model = NCF(d.user_num, d.item_num, 32, 3, 0.0, "NeuMF-end").to(dev())
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    st = EpochStream(d.pos_user, d.pos_item, d.user_num, d.item_num, num_ng=4, seed=3)
+    st.begin_epoch(0)
+    u = torch.empty(B, dtype=torch.int64, device=dev())
+    i = torch.empty(B, dtype=torch.int64, device=dev())
+    y = torch.empty(B, dtype=torch.float32, device=dev())
+    st.fill(0, B, u, i, y)
+    ts.step(u, i, y)
+    loss = ts.pop_loss()
+    assert abs(loss - np.log(2)) < 0.05
+    assert float(ts.grads.flat.abs().max()) == 0.0 and ts.grads.touched_count.tolist() == [0, 0]
+    ts.flush()
+    after = model.state_dict()
+    touched_u = torch.zeros(d.user_num, dtype=torch.bool, device=dev())
+    touched_u[u] = True
+    du = (after["embed_user_MLP.weight"] - before["embed_user_MLP.weight"]).abs().amax(dim=1)
+    assert float(du[~touched_u].max()) == 0.0                    # rows outside the batch are untouched
+    assert float(du[touched_u].min()) > 0.0 and float(du[touched_u].max()) <= 1.0001e-3   # |Adam step 1| <= lr
+    snap = {k: v.clone() for k, v in after.items()}
+    ts._dirty = True
+    ts.flush()                                                   # idempotent
+    assert all(torch.equal(snap[k], v) for k, v in model.state_dict().items())
+
+
+def test_eval_at_full_size_and_reference_call_path(ml20m):
+    """138 493 users x 100 candidates in one call; HR is a function of the rank only; and
+    `metrics(model, DataLoader(NCFData(test_data), batch_size=100), k)` — the reference call
+    (scripts/train_neumf.py:56,125) — returns the same lists."""
+    import torch.utils.data as data
+    from ncf_b200.datasets import NCFData
+    from ncf_b200.metrics import evaluate, metrics
+    from ncf_b200.models import NCF
+    d = ml20m
+    torch.manual_seed(1)
+    model = NCF(d.user_num, d.item_num, 32, 3, 0.0, "NeuMF-end").to(dev()).eval()
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.startswith("embed_"):
+                p.mul_(30.0)
+    res = evaluate(model, d.test_users, d.test_cands, 10)
+    rank = res.rank
+    assert torch.equal(res.hit.bool(), rank >= 0) and int(rank.max()) <= 9
+    # rank of the held-out item == number of strictly better candidates (ties to the lower index = it wins)
+    better = (res.scores[:, 1:] > res.scores[:, :1]).sum(dim=1)
+    assert torch.equal(torch.where(better < 10, better, torch.full_like(better, -1)).int(), rank)
+    assert torch.equal(res.topk[:, 0].long(), res.scores.argmax(dim=1))
+    # reference-style call on a slice (the list-of-pairs test_data layout of datasets.py:26-35)
+    n = 2000
+    pairs = torch.stack([d.test_users[:n, None].expand(-1, 100), d.test_cands[:n]], dim=2).reshape(-1, 2)
+    loader = data.DataLoader(NCFData(pairs.cpu().numpy(), d.item_num, None, 0, False), batch_size=100,
+                             shuffle=False, num_workers=0)
+    HR, NDCG = metrics(model, loader, 10)
+    assert HR == (rank[:n] >= 0).int().tolist()
+    assert NDCG == [0.0 if r < 0 else float(1.0 / np.log2(r + 2)) for r in rank[:n].tolist()]
+
+
+def test_ncfdata_ng_sample_reference_semantics():
+    """NCFData(...).ng_sample() on the GPU keeps the reference's observable behaviour
+    (src/data/datasets.py:53-83): features_fill = positives then negatives, labels 1..1,0..0,
+    len(dataset) = (num_ng+1) * P, negatives never collide with train_mat."""
+    from ncf_b200.datasets import NCFData, TrainMatrix
+    rng = np.random.default_rng(0)
+    U, I, num_ng = 50, 40, 4
+    pairs = np.unique(np.stack([rng.integers(0, U, 600), rng.integers(0, I, 600)], 1), axis=0)
+    mat = TrainMatrix(pairs, U, I)
+    ds = NCFData(pairs.tolist(), I, mat, num_ng, True, device="cuda:0", seed=5)
+    ds.ng_sample()
+    P = len(pairs)
+    assert len(ds) == (num_ng + 1) * P
+    assert (ds.features_fill[:P] == pairs).all() and (ds.labels_fill[:P] == 1).all() and (ds.labels_fill[P:] == 0).all()
+    assert (ds.features_fill[P:, 0] == np.repeat(pairs[:, 0], num_ng)).all()
+    assert not any((int(u), int(j)) in mat for u, j in ds.features_fill[P:])
+    first = ds.features_fill[P:].copy()
+    ds.ng_sample()                                               # a new epoch draws new negatives
+    assert (ds.features_fill[P:, 1] != first[:, 1]).mean() > 0.5
+    assert ds[0] == (int(pairs[0, 0]), int(pairs[0, 1]), 1) and ds[P][2] == 0
