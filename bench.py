@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (synthetic shape, factor_num, num_layers, batch)
     "ml20m": ("ml20m", 32, 3, 65536),
     "ml1m": ("ml1m", 8, 3, 256),
+    "big": ("big", 64, 3, 65536),      # BASELINE configs[4]: row-sharded at N>1
 }
 METRIC, UNIT = "NeuMF train samples/s", "samples/s"
 
@@ -168,7 +169,9 @@ def config_dict(workload, n_gpus):
     U, I, total, _ = SHAPES[shape]
     return {"workload": f"NeuMF f={f} L={L} (tower {f << L}->{f}) on synthetic {shape} shape "
                         f"({U} users x {I} items, ~{total} interactions, 4 neg/pos), batch {B} per GPU, Adam lr 1e-3",
-            "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus}",
+            "batch_per_gpu": B, "global_batch": B * n_gpus,
+            "parallelism": (f"row-sharded tables x{n_gpus} (all-to-all)" if workload == "big" and n_gpus > 1
+                            else f"dp{n_gpus}"),
             "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
                   "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
 
@@ -195,24 +198,49 @@ def run_ours(args):
     shape, f, L, B = WORKLOADS[args.workload]
     K, W = args.steps, max(3, args.warmup)
 
-    inter = make_interactions(shape, device=dev)
-    U, I = inter.user_num, inter.item_num
-    torch.manual_seed(0)
-    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
-    model.tower_math = args.tower_math
-    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
-    # every rank draws from its own slice of the epoch stream (weak scaling: B per GPU per step)
-    stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=20250605)
-    stream.begin_epoch(0)
     n_batches = W + K
     need = n_batches * B
-    q0 = rank * need
-    if q0 + need > stream.S:
-        raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
-    bu = torch.empty(need, dtype=torch.int64, device=dev)
-    bi = torch.empty(need, dtype=torch.int64, device=dev)
-    bl = torch.empty(need, dtype=torch.float32, device=dev)
-    stream.fill(q0, need, bu, bi, bl)
+    sharded = None
+    if args.workload == "big":
+        # BASELINE configs[4]: 10M users x 1M items, f=64.  Batches are drawn directly (uniform users,
+        # Zipf-like items); at N>1 the tables are row-sharded and every rank draws its own users.
+        from ncf_b200.synth import SHAPES
+        from ncf_b200.dist import RowShardedTrainer, shard_rows
+        inter = None
+        U, I = SHAPES["big"][0], SHAPES["big"][1]
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        Ul, Il = shard_rows(U, world, rank), shard_rows(I, world, rank)
+        torch.manual_seed(0)
+        with torch.device(dev):
+            model = NCF(Ul, Il, f, L, 0.0, "NeuMF-end")
+        model.tower_math = args.tower_math
+        # samples are partitioned by user (RowShardedTrainer: sharding follows the data); items are global
+        bu = torch.randint(0, Ul, (need,), device=dev, generator=g) * world + rank
+        zipf = torch.rand(need, device=dev, generator=g).pow(3.0)                      # popularity skew
+        bi = (zipf * I).long().clamp_(0, I - 1)
+        bl = (torch.rand(need, device=dev, generator=g) < 0.2).float()
+        if world > 1:
+            sharded = RowShardedTrainer(model, U, I, lr=1e-3, max_batch=B)
+            ts = sharded.ts
+        else:
+            ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    else:
+        inter = make_interactions(shape, device=dev)
+        U, I = inter.user_num, inter.item_num
+        torch.manual_seed(0)
+        model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
+        model.tower_math = args.tower_math
+        ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+        # every rank draws from its own slice of the epoch stream (weak scaling: B per GPU per step)
+        stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=20250605)
+        stream.begin_epoch(0)
+        q0 = rank * need
+        if q0 + need > stream.S:
+            raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
+        bu = torch.empty(need, dtype=torch.int64, device=dev)
+        bi = torch.empty(need, dtype=torch.int64, device=dev)
+        bl = torch.empty(need, dtype=torch.float32, device=dev)
+        stream.fill(q0, need, bu, bi, bl)
     sl = lambda k: slice(k * B, (k + 1) * B)
 
     def barrier():
@@ -227,7 +255,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sync_grads = make_dp_sync(ts, world) if world > 1 else None
+    if sharded is not None:
+        sync_grads = sharded.step
+    else:
+        sync_grads = make_dp_sync(ts, world) if world > 1 else None
 
     def one_step(k):
         if sync_grads is None:
@@ -250,7 +281,9 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * K * B / (ms_total * 1e-3)
-    launches_per_step = 7  # mark, catch-up, weight split, fused tile, row Adam, tower Adam, finalize
+    # mark, catch-up, weight split, fused tile, row Adam, tower Adam, finalize; the row-sharded step adds
+    # bucket count/scan/place, a second mark, 2 gathers, 2 permutes and 2 scatter-adds (NCCL kernels not counted)
+    launches_per_step = 17 if sharded is not None else 7
 
     # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
     phases = None
@@ -286,7 +319,7 @@ def run_ours(args):
             ts.step(du, di, dl)
         else:
             sync_grads(du, di, dl)
-        host_loss.copy_(ts.loss_accum, non_blocking=True)
+        host_loss.copy_(sharded.loss_accum if sharded is not None else ts.loss_accum, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the reference reads loss.item() every step
         return float(host_loss[0])
 
@@ -349,7 +382,7 @@ def run_ours(args):
 
     # ---- evaluation throughput (second half of the metric: eval users/s) -----------------------------------
     eval_info = None
-    if world == 1:
+    if world == 1 and inter is not None:
         from ncf_b200.metrics import evaluate
         ts.flush()
         model.eval()
@@ -369,7 +402,7 @@ def run_ours(args):
 
     # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only) ---------------------------
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and inter is not None:   # dense CPU Adam over 10M rows: not bounded
         sps, ms, done, cores = cpu_reference_run(args.workload, steps=40, warmup=1, budget_s=15.0)
         cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{done} steps of batch {B} ({ms:.0f} ms/step) of the same config: reference op "

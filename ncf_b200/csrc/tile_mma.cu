@@ -18,6 +18,8 @@
 // embedding-row gradients leave the CTA as vector REDs (dW_k is small and L2-resident).
 //
 // Replaces reference src/ncf/models.py:97-118 and scripts/train_neumf.py:112-114.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tile_params.cuh"
 
@@ -689,6 +691,8 @@ namespace ncf {
 
 // 0 = not eligible, else the tile height (64 or 32).
 int mma_tile_rows(const TileParams& p_in) {
+  static const int min_f = getenv("NCF_MMA_MIN_F") ? atoi(getenv("NCF_MMA_MIN_F")) : 8;  // tuning knob
+  if (p_in.f < min_f) return 0;
   if (p_in.type == NCF_GMF) return 0;          // no tower: the generic kernel is already a pure gather
   if (p_in.f < 8 || (p_in.f & (p_in.f - 1)) != 0) return 0;  // block shapes assume power-of-two widths
   TileParams p = p_in;

@@ -20,6 +20,7 @@ SHAPES = {
     "ml100k": (943, 1682, 100_000, 20250603),
     "ml1m": (6040, 3706, 1_000_209, 20250604),
     "ml20m": (138_493, 26_744, 20_000_263, 20250605),
+    "big": (10_000_000, 1_000_000, 1_000_000_000, 20250606),   # table shape only (bench draws batches directly)
 }
 
 
