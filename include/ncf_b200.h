@@ -111,6 +111,9 @@ typedef struct NcfAdamHyper {
 /* ---- library ------------------------------------------------------------------------- */
 int ncf_version(void);
 const char* ncf_last_error(void);
+/* which tile-kernel family the calling thread's last forward / training call ran on:
+ * 0 none yet, 1 generic (FMA), 2 mma.sync tensor path, 3 tcgen05/TMEM path (diagnostic; tests) */
+int ncf_last_tile_path(void);
 /* number of floats in the flat tower buffer for this shape */
 int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num, int32_t num_layers);
 

@@ -55,6 +55,7 @@ _i64, _i32, _u64, _vp, _fl = C.c_int64, C.c_int32, C.c_uint64, C.c_void_p, C.c_f
 SIGNATURES = {
     "ncf_version": (C.c_int, []),
     "ncf_last_error": (C.c_char_p, []),
+    "ncf_last_tile_path": (C.c_int, []),
     "ncf_tower_param_count": (_i64, [_i32, _i32, _i32]),
     "ncf_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "ncf_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),

@@ -6,6 +6,7 @@
 namespace ncf {
 
 static thread_local char g_err[512] = "";
+thread_local int g_tile_path = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -59,6 +60,8 @@ int validate_model(const NcfModel* m) {
 extern "C" int ncf_version(void) { return NCF_ABI_VERSION; }
 
 extern "C" const char* ncf_last_error(void) { return ncf::g_err; }
+
+extern "C" int ncf_last_tile_path(void) { return ncf::g_tile_path; }
 
 extern "C" int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num,
                                          int32_t num_layers) {

@@ -1,4 +1,6 @@
 // C-ABI entry points for the forward pass, the loss and the fused training step.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tile_params.cuh"
 
@@ -54,6 +56,16 @@ namespace ncf {
 // path needs mma_split_floats(p) floats of workspace for the pre-split weights.
 int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t workspace_bytes,
                      cudaStream_t st) {
+  if (umma_eligible(p)) {
+    const int64_t need = umma_forward_workspace_floats(p, p.B) * 4;
+    if (!workspace || workspace_bytes < need) {
+      set_error("forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+      return NCF_ERR_WORKSPACE;
+    }
+    g_tile_path = 3;
+    return launch_umma_forward(p, tower_passes(m), (float*)workspace, st);
+  }
+  g_tile_path = mma_tile_rows(p) == 0 ? 1 : 2;
   if (mma_tile_rows(p) == 0) return launch_generic_forward(p, st);
   const int64_t need = mma_split_floats(p) * 4;
   if (!workspace || workspace_bytes < need) {
@@ -68,11 +80,14 @@ int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t 
 }  // namespace ncf
 
 extern "C" int64_t ncf_forward_workspace_bytes(const NcfModel* m, int64_t B) {
-  (void)B;
   if (ncf::validate_model(m) != NCF_OK) return -1;
   TileParams p{};
   ncf::fill_model_params(p, m);
-  return ncf::mma_tile_rows(p) ? ncf::align_up(ncf::mma_split_floats(p) * 4, 256) : 0;
+  p.B = B;
+  int64_t bytes = ncf::mma_tile_rows(p) ? ncf::align_up(ncf::mma_split_floats(p) * 4, 256) : 0;
+  if (ncf::umma_eligible(p))
+    bytes = std::max(bytes, ncf::align_up(ncf::umma_forward_workspace_floats(p, B) * 4, 256) + 256);
+  return bytes;
 }
 
 extern "C" int ncf_forward(const NcfModel* m, const int64_t* user, const int64_t* item, int64_t B,
@@ -109,7 +124,9 @@ extern "C" int64_t ncf_train_workspace_bytes(const NcfModel* m, int64_t B) {
   if (ncf::validate_model(m) != NCF_OK || B < 0) return -1;
   TileParams p{};
   ncf::fill_model_params(p, m);
-  const int64_t floats = ncf::mma_tile_rows(p) ? ncf::mma_split_floats(p) : scratch_floats(m, B);
+  p.B = B;
+  int64_t floats = ncf::mma_tile_rows(p) ? ncf::mma_split_floats(p) : scratch_floats(m, B);
+  if (ncf::umma_eligible(p)) floats = std::max(floats, ncf::umma_train_workspace_floats(p, B));
   return ncf::align_up(floats * 4, 256) + 256;
 }
 
@@ -183,6 +200,11 @@ static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* use
   p.invB = 1.f / (float)(B_norm > 0 ? B_norm : B);  // mean over the (global) batch
   p.logits = logits_out;
   p.loss_accum = loss_accum;
+  if (ncf::umma_eligible(p)) {
+    ncf::g_tile_path = 3;
+    return ncf::launch_umma_train(p, ncf::tower_passes(m), (float*)workspace, (cudaStream_t)stream);
+  }
+  ncf::g_tile_path = ncf::mma_tile_rows(p) != 0 ? 2 : 1;
   if (ncf::mma_tile_rows(p) != 0) {
     rc = ncf::mma_prepare_weights(p, (float*)workspace, (cudaStream_t)stream);
     if (rc != NCF_OK) return rc;

@@ -1,0 +1,148 @@
+"""GPU parity of the tcgen05/TMEM tower path (ncf_b200/csrc/tile_umma.cu).
+
+The path is selected for large batches only (NCF_UMMA_MIN_B, default 8192); these tests lower the
+threshold so that the small reference goldens and oracle-sized batches run through it, and check
+through ncf_last_tile_path() that they really did.  Same bar as tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncf_numpy as onp
+from tests import test_gpu_parity as tp
+from tests.util import assert_close, assert_close_adam
+
+pytestmark = pytest.mark.gpu
+
+UMMA_CASES = ["train_neumf_f32_l2", "train_neumf_f64_l3"]
+
+
+@pytest.fixture
+def force_umma(monkeypatch):
+    monkeypatch.setenv("NCF_UMMA_MIN_B", "1")
+    yield
+    from ncf_b200 import _lib
+    assert _lib.load().ncf_last_tile_path() == 3, "the tcgen05 path did not run"
+
+
+@pytest.mark.parametrize("name", UMMA_CASES)
+def test_forward_matches_reference(force_umma, name):
+    tp.test_forward_matches_reference(name)
+
+
+@pytest.mark.parametrize("name", UMMA_CASES)
+def test_fused_step_gradients_match_reference(force_umma, name):
+    tp.test_fused_step_gradients_match_reference(name)
+
+
+@pytest.mark.parametrize("name", UMMA_CASES)
+def test_training_steps_match_reference(force_umma, name):
+    tp.test_training_steps_match_reference(name)
+
+
+def _near_relu_kink(params, u, i, L, tol=1e-5):
+    """Samples with a tower pre-activation within rounding distance of 0: relu'(z) there depends on
+    the last bit of z, so two correct fp32 implementations may legitimately disagree on it."""
+    x = np.concatenate([params["embed_user_MLP.weight"][u], params["embed_item_MLP.weight"][i]], 1).astype(np.float64)
+    near = np.zeros(len(u), bool)
+    for k in range(L):
+        w = params[f"MLP_layers.{3 * k + 1}.weight"].astype(np.float64)
+        b = params[f"MLP_layers.{3 * k + 1}.bias"].astype(np.float64)
+        z = x @ w.T + b
+        near |= (np.abs(z) < tol * np.abs(z).max()).any(1)
+        x = np.maximum(z, 0.0)
+    return near
+
+
+def _oracle_case(model_type, f, L, B, U=700, I=500, seed=0, bad_rows=()):
+    from ncf_b200 import ops
+    from ncf_b200.models import NCF
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    model = NCF(U, I, f, L, 0.0, model_type).to(tp.dev())
+    with torch.no_grad():  # biases are zero-initialised by the reference; make them matter
+        for lin in model.linears():
+            lin.bias.uniform_(-0.1, 0.1)
+    params = tp.state_np(model)
+    u = rng.integers(0, U, B)
+    i = rng.integers(0, I, B)
+    y = (rng.random(B) < 0.3).astype(np.float32)
+    keep = ~_near_relu_kink(params, u, i, L)
+    assert keep.sum() >= B - 8
+    u, i, y = u[keep], i[keep], y[keep]
+    B = int(keep.sum())
+    ud, idd, yd = (torch.from_numpy(a).to(tp.dev()) for a in (u, i, y))
+    mt = model.abi_type()
+    g = ops.GradBuffers.allocate(mt, f, L, U, I, B, tp.dev())
+    m = model.abi_struct()
+    ws = torch.empty(ops.train_workspace_bytes(m, B), dtype=torch.uint8, device=tp.dev())
+    loss = torch.zeros(1, dtype=torch.float64, device=tp.dev())
+    logits = torch.empty(B, device=tp.dev())
+    ops.mark_rows(m, g.struct(), ud, idd)
+    ops.train_step_grads(m, g.struct(), ud, idd, yd, None, 1.0, loss, ws, logits)
+    torch.cuda.synchronize()
+    ref_logits = onp.forward(params, u, i, model_type)
+    ref_loss, dl = onp.loss_and_dlogit(ref_logits, y)
+    ref = onp.backward(params, u, i, model_type, dl)
+    assert_close(logits.cpu().numpy(), ref_logits, "logits")
+    assert abs(float(loss.item()) - ref_loss) <= 5e-6 * abs(ref_loss)
+    return model, g, ref, None
+
+
+def _check_grads(model, g, ref):
+    """Same walk over the gradient buffers as tests/test_gpu_parity.py."""
+    tables = {"embed_user_GMF.weight": g.g_user_gmf, "embed_item_GMF.weight": g.g_item_gmf,
+              "embed_user_MLP.weight": g.g_user_mlp, "embed_item_MLP.weight": g.g_item_mlp}
+    for k, buf in tables.items():
+        if k in ref:
+            assert_close(buf.cpu().numpy(), ref[k], f"grad {k}")
+    flat = g.g_tower.cpu().numpy()
+    off = 0
+    keys = [f"MLP_layers.{3 * k + 1}.{s}" for k in range(model.num_layers) for s in ("weight", "bias")]
+    keys += ["predict_layer.weight", "predict_layer.bias"]
+    sd = model.state_dict()
+    for k in keys:
+        n = sd[k].numel()
+        piece = flat[off:off + n].reshape(tuple(sd[k].shape))
+        off += n
+        assert_close(piece, ref[k], f"grad {k}")
+    assert off == flat.size
+
+
+@pytest.mark.parametrize("model_type,f,L,B", [("NeuMF-end", 32, 3, 3000), ("MLP", 32, 2, 1111),
+                                              ("NeuMF-end", 64, 3, 700), ("NeuMF-end", 32, 1, 257)])
+def test_step_matches_oracle(force_umma, model_type, f, L, B):
+    model, g, ref, _ = _oracle_case(model_type, f, L, B)
+    _check_grads(model, g, ref)
+
+
+def test_tf32_mode_is_close(force_umma):
+    """tower_math='tf32' (one MMA per product) stays within TF32 rounding of the oracle."""
+    from ncf_b200.models import NCF
+    torch.manual_seed(1)
+    rng = np.random.default_rng(1)
+    U, I, f, L, B = 300, 200, 32, 3, 1000
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(tp.dev()).eval()
+    model.tower_math = "tf32"
+    u = rng.integers(0, U, B)
+    i = rng.integers(0, I, B)
+    with torch.no_grad():
+        got = model(torch.from_numpy(u).to(tp.dev()), torch.from_numpy(i).to(tp.dev())).cpu().numpy()
+    ref = onp.forward(tp.state_np(model), u, i, "NeuMF-end")
+    assert np.max(np.abs(got - ref)) <= 5e-3 * np.max(np.abs(ref))
+
+
+def test_invalid_indices_give_nan_and_no_gradient(force_umma):
+    from ncf_b200.models import NCF
+    torch.manual_seed(2)
+    U, I, f, L, B = 100, 80, 32, 2, 300
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(tp.dev()).eval()
+    u = torch.randint(0, U, (B,), device=tp.dev())
+    i = torch.randint(0, I, (B,), device=tp.dev())
+    u[5] = U
+    i[200] = -1
+    with torch.no_grad():
+        out = model(u, i).cpu().numpy()
+    bad = np.zeros(B, bool)
+    bad[[5, 200]] = True
+    assert np.isnan(out[bad]).all() and np.isfinite(out[~bad]).all()

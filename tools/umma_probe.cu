@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   const bool a_mn = (mode == 1 || mode == 2 || mode == 3 || mode == 5);
   const bool b_mn = (mode == 1 || mode == 2 || mode == 4 || mode == 6);
   const bool swp = (mode == 2 || mode == 5 || mode == 6);
-  if (mode == 7) {            // K-major, SWIZZLE_128B: rows = M/N, cols = K (one 32-column panel)
+  if (mode == 7 || mode == 10) {            // K-major, SWIZZLE_128B: rows = M/N, cols = K (one 32-column panel)
     fill_swizzled(a_img, A, M, K, K, 0);
     fill_swizzled(b_img, B, N, K, K, 0);
-  } else if (mode >= 8) {     // MN-major: rows = K, cols = M/N; 8: SWIZZLE_128B, 9: 128B_BASE32B
+  } else if (mode == 8 || mode == 9) {     // MN-major: rows = K, cols = M/N; 8: SWIZZLE_128B, 9: 128B_BASE32B
     fill_swizzled(a_img, A, K, M, M, mode == 9);
     fill_swizzled(b_img, B, K, N, N, mode == 9);
   } else {
@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   const uint32_t tmem = tmem_base;
 
   if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc(M, N, a_mn || mode >= 8, b_mn || mode >= 8);
+    const uint32_t idesc = make_idesc(M, N, a_mn || mode == 8 || mode == 9, b_mn || mode == 8 || mode == 9);
     for (int ks = 0; ks < K / 8; ++ks) {
       uint64_t da, db;
-      if (mode == 7) {
+      if (mode == 7 || mode == 10) {
         // K-major SW128: 8-row groups 1024 B apart (SBO); the k-step advances 32 B inside the 128-B row
         da = make_desc(smem_u32(a_img) + ks * 32, 16, 1024, 2);
         db = make_desc(smem_u32(b_img) + ks * 32, 16, 1024, 2);
@@ -192,9 +192,14 @@ int main() {
   const size_t smem = sizeof(float) * (M * K + N * K);
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int rc = 0;
-  for (int mode = 0; mode < 10; ++mode) {
-    cudaMemcpy(dA, (mode==1||mode==2||mode==3||mode==5||mode>=8) ? At.data() : A.data(), sizeof(float) * M * K, cudaMemcpyHostToDevice);
-    cudaMemcpy(dB, (mode==1||mode==2||mode==4||mode==6||mode>=8) ? Bt.data() : B.data(), sizeof(float) * N * K, cudaMemcpyHostToDevice);
+  for (int mode = 0; mode < 11; ++mode) {
+    // mode 10: operands carry 0.75 ulp(tf32) of extra low mantissa bits; the result equals the exact
+    // one iff the tensor core TRUNCATES fp32 -> tf32 (round-to-nearest would move every operand up)
+    std::vector<float> Alow(A), Blow(B);
+    for (auto& v : Alow) { uint32_t u; memcpy(&u, &v, 4); u |= 0x1800u; memcpy(&v, &u, 4); }
+    for (auto& v : Blow) { uint32_t u; memcpy(&u, &v, 4); u |= 0x1800u; memcpy(&v, &u, 4); }
+    cudaMemcpy(dA, mode == 10 ? Alow.data() : (mode==1||mode==2||mode==3||mode==5||mode==8||mode==9) ? At.data() : A.data(), sizeof(float) * M * K, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, mode == 10 ? Blow.data() : (mode==1||mode==2||mode==4||mode==6||mode==8||mode==9) ? Bt.data() : B.data(), sizeof(float) * N * K, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0, sizeof(float) * M * N); cudaMemset(dS, 0, sizeof(int));
     probe_kernel<<<1, 128, smem>>>(dA, dB, dD, mode, dS);
     cudaError_t e = cudaDeviceSynchronize();
