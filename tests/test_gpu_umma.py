@@ -40,7 +40,7 @@ def test_training_steps_match_reference(force_umma, name):
     tp.test_training_steps_match_reference(name)
 
 
-def _near_relu_kink(params, u, i, L, tol=1e-5):
+def _near_relu_kink(params, u, i, L, tol=3e-6):
     """Samples with a tower pre-activation within rounding distance of 0: relu'(z) there depends on
     the last bit of z, so two correct fp32 implementations may legitimately disagree on it."""
     x = np.concatenate([params["embed_user_MLP.weight"][u], params["embed_item_MLP.weight"][i]], 1).astype(np.float64)
@@ -68,7 +68,7 @@ def _oracle_case(model_type, f, L, B, U=700, I=500, seed=0, bad_rows=()):
     i = rng.integers(0, I, B)
     y = (rng.random(B) < 0.3).astype(np.float32)
     keep = ~_near_relu_kink(params, u, i, L)
-    assert keep.sum() >= B - 8
+    assert keep.sum() >= B - 32
     u, i, y = u[keep], i[keep], y[keep]
     B = int(keep.sum())
     ud, idd, yd = (torch.from_numpy(a).to(tp.dev()) for a in (u, i, y))
