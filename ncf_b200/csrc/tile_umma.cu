@@ -30,9 +30,9 @@ namespace {
 
 constexpr int kTile = 128;  // samples per accumulator tile (UMMA M)
 constexpr uint32_t kHiMask = 0xffffe000u;
-constexpr int kProducerWarps = 8;
-constexpr int kDepth = 3;           // panels of loads in flight per producer thread
-constexpr int kGemmThreads = 544;   // warps 0-7 producers, 8 MMA, 9-12 / 13-16 epilogue (even / odd tiles)
+constexpr int kProducerWarps = 8;   // two groups of four (even / odd panels)
+constexpr int kLoaderWarp = 17;     // weight-panel bulk copies
+constexpr int kGemmThreads = 576;   // warps 0-7 A producers, 8 MMA, 9-12 / 13-16 epilogue (even / odd tiles), 17 loader
 constexpr int kChunk = 32;          // samples per wgrad stage (4 k-steps of 8)
 constexpr int kMaxStages = 4;
 
@@ -86,6 +86,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     if (done) return;
   }
   __trap();
+}
+// Non-blocking probe of a phase, warp-uniform result.
+__device__ __forceinline__ bool mbar_test_warp(uint64_t* b, uint32_t parity) {
+  uint32_t done = 0;
+  if ((threadIdx.x & 31) == 0)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return __shfl_sync(0xffffffffu, done, 0) != 0;
 }
 // One lane polls / arrives for its warp: 32 arrivals on one mbarrier serialise in shared memory.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* b, uint32_t parity) {
@@ -243,7 +252,7 @@ umma_gemm_kernel(const __grid_constant__ TileParams p, const __grid_constant__ G
   while (tmem_cols < 2u * N) tmem_cols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < g.stages; ++s) { mbar_init(&bars.full[s], kProducerWarps + 1); mbar_init(&bars.empty[s], 1); }
+    for (int s = 0; s < g.stages; ++s) { mbar_init(&bars.full[s], kProducerWarps / 2 + 1); mbar_init(&bars.empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -259,62 +268,126 @@ umma_gemm_kernel(const __grid_constant__ TileParams p, const __grid_constant__ G
   const uint32_t tmem = bars.tmem_base;
 
   if (warp < kProducerWarps) {
-    // ===== producers: two threads per sample row, each moves 64 B of every 128-byte panel row; the
-    // (tile, panel) sequence is one flat software pipeline with kDepth panels of loads in flight ===========
-    const int t = tid, r = t >> 1, h = t & 1;
+    // ===== A producers.  Two groups of four warps take alternate panels of the flat (tile, panel)
+    // sequence, so two hand-off chains (wait -> copy -> split -> fence -> arrive) run concurrently.
+    // A thread copies global -> shared with cp.async (raw fp32 is the "hi" image: the tensor core
+    // ignores the low 13 mantissa bits) and later derives the "lo" image from its own pieces.
+    const int grp = warp >> 2;        // parity of the panels this group serves
+    const int u = tid & 127;          // thread within the group: rows r0 and r0 + 64,
+    const int r0 = u >> 1, hq = u & 1;  // 16-byte pieces 2c + hq (a lane pair covers one 32-byte sector)
     const int d = p.d;
     const int64_t my_tiles = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_iter = my_tiles * panels;
-    // load-side cursor
-    int64_t ld_tl = 0;
-    int ld_pi = 0;
-    bool ld_ok = false;
-    const float *ld_u = nullptr, *ld_i = nullptr;
-    int64_t pre_u = -1, pre_it = -1;  // indices of the load cursor's NEXT tile, fetched one tile early
-    auto fetch_idx = [&](int64_t tl) {
-      pre_u = -1;
-      pre_it = -1;
-      if (tl < my_tiles) {
-        const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + r;
-        if (row < p.B) {
-          pre_u = p.user[p.user_div > 0 ? row / p.user_div : row];
-          pre_it = p.item[row];
+    const int64_t n_own = (n_iter + 1 - grp) / 2;
+    const int tile_step = (panels == 1) ? 2 : 1;  // distance to the next tile this group touches
+    // issue cursor
+    int64_t is_tl = 0, cur_tl = -1;
+    int is_pi = grp, is_s = grp, cs = grp;
+    uint32_t is_ph = 0;
+    while (is_pi >= panels) { is_pi -= panels; ++is_tl; }
+    bool ok[2] = {false, false};
+    const float *src_u[2] = {nullptr, nullptr}, *src_i[2] = {nullptr, nullptr};
+    int64_t pre_u[2] = {-1, -1}, pre_it[2] = {-1, -1};  // indices of the group's next tile, fetched a tile early
+    auto prefetch_idx = [&](int64_t tl) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        pre_u[j] = -1;
+        pre_it[j] = -1;
+        const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + r0 + 64 * j;
+        if (tl < my_tiles && row < p.B) {
+          pre_u[j] = p.user[p.user_div > 0 ? row / p.user_div : row];
+          pre_it[j] = p.item[row];
         }
       }
     };
     auto enter_tile = [&](int64_t tl) {
-      const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + r;
-      ld_ok = row < p.B;
-      if (g.gather) {
-        const int64_t u = pre_u, it = pre_it;
-        if (u < 0 || u >= p.U || it < 0 || it >= p.I) ld_ok = false;
-        else { ld_u = p.eum + u * d; ld_i = p.eim + it * d; }
-        fetch_idx(tl + 1);
-      } else if (ld_ok) {
-        ld_u = g.a + row * (int64_t)K;
-      }
-    };
-    auto issue = [&](float4 (&v)[4]) {
-      if (ld_pi == 0) enter_tile(ld_tl);
-      const int c0 = ld_pi * 32 + h * 16;
-      const float* src = nullptr;
-      if (ld_ok && !(g.ablate & 1)) src = g.gather ? (c0 < d ? ld_u + c0 : ld_i + (c0 - d)) : ld_u + c0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (src != nullptr && c0 + c * 4 < K) v[c] = ldg4(src + c * 4);
-        else v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 2; ++j) {
+        const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + r0 + 64 * j;
+        ok[j] = row < p.B;
+        if (g.gather) {
+          const int64_t uu = pre_u[j], it = pre_it[j];
+          if (uu < 0 || uu >= p.U || it < 0 || it >= p.I) ok[j] = false;
+          else { src_u[j] = p.eum + uu * d; src_i[j] = p.eim + it * d; }
+        } else if (ok[j]) {
+          src_u[j] = g.a + row * (int64_t)K;
+        }
       }
-      if (++ld_pi == panels) { ld_pi = 0; ++ld_tl; }
+      if (g.gather) prefetch_idx(tl + tile_step);
     };
-    int st_pi = 0, s = 0;
-    uint32_t ph = 0;
+    // blocking == false: copy only if the stage is already free (returns whether it did)
+    auto issue = [&](bool blocking) -> bool {
+      if (blocking) mbar_wait_warp(&bars.empty[is_s], is_ph ^ 1);
+      else if (!mbar_test_warp(&bars.empty[is_s], is_ph ^ 1)) return false;
+      if (is_tl != cur_tl) { enter_tile(is_tl); cur_tl = is_tl; }
+      uint8_t* st = smem + (size_t)is_s * stage_bytes;
+      const int c0 = is_pi * 32;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = r0 + 64 * j;
+        const float* src = nullptr;
+        if (ok[j] && !(g.ablate & 1)) src = g.gather ? (c0 < d ? src_u[j] + c0 : src_i[j] + (c0 - d)) : src_u[j] + c0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int piece = 2 * c + hq;
+          const bool valid = src != nullptr && c0 + piece * 4 < K;
+          cp_async16_zfill(st + r * 128 + ((piece ^ (r & 7)) << 4), valid ? src + piece * 4 : g.b_img, valid);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      is_pi += 2;
+      while (is_pi >= panels) { is_pi -= panels; ++is_tl; }
+      is_s += 2;
+      if (is_s >= g.stages) { is_s -= g.stages; is_ph ^= 1; }
+      return true;
+    };
     int tr = 0;
-    auto consume = [&](const float4 (&v)[4]) {
-      mbar_wait_warp(&bars.empty[s], ph ^ 1);
-      if (t == 0) NCF_TRACE(0, tr);
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      if (t == 0) {
-        const float* bsrc = g.b_img + (int64_t)st_pi * 2 * g.n_total * 32 + (int64_t)nb * N * 32;
+    auto consume = [&](bool more_pending) {
+      if (more_pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (u == 0 && grp == 0) NCF_TRACE(0, tr);
+      uint8_t* st = smem + (size_t)cs * stage_bytes;
+      if (g.passes == 3 && !(g.ablate & 16)) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int r = r0 + 64 * j;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int off = r * 128 + (((2 * c + hq) ^ (r & 7)) << 4);
+            float4 hi, lo;
+            split4(*reinterpret_cast<const float4*>(st + off), hi, lo);
+            *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+          }
+        }
+      }
+      fence_async_smem();
+      if (u == 0 && grp == 0) NCF_TRACE(0, tr + 1);
+      tr += 2;
+      mbar_arrive_warp(&bars.full[cs]);
+      cs += 2;
+      if (cs >= g.stages) cs -= g.stages;
+    };
+    if (g.gather) prefetch_idx(is_tl);
+    // The next own panel is copied before this one is split only when its stage is already free:
+    // a blocking wait there would hold back the hand-off of the panel the MMA warp is waiting for.
+    if (n_own > 0) issue(true);
+    for (int64_t k = 0; k < n_own; ++k) {
+      const bool more = k + 1 < n_own;
+      const bool early = more && g.stages >= 3 && issue(false);
+      consume(early);
+      if (more && !early) issue(true);
+    }
+  } else if (warp == kLoaderWarp) {
+    // ===== weight-panel loader: one thread, bulk copies of the pre-split (hi, lo) images ======================
+    if (lane == 0) {
+      const int64_t my_tiles = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int64_t n_iter = my_tiles * panels;
+      int s = 0, pi = 0;
+      uint32_t ph = 0;
+      for (int64_t i = 0; i < n_iter; ++i) {
+        mbar_wait(&bars.empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const float* bsrc = g.b_img + (int64_t)pi * 2 * g.n_total * 32 + (int64_t)nb * N * 32;
         if (g.ablate & 2) {
           mbar_arrive(&bars.full[s]);
         } else if (g.passes == 3) {
@@ -325,38 +398,8 @@ umma_gemm_kernel(const __grid_constant__ TileParams p, const __grid_constant__ G
           mbar_expect_tx(&bars.full[s], b_bytes);
           bulk_g2s(st + 2 * a_bytes, bsrc, b_bytes, &bars.full[s]);
         }
-      }
-      uint8_t* a_hi = st + r * 128;
-      uint8_t* a_lo = a_hi + a_bytes;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float4 hi, lo;
-        split4(v[c], hi, lo);
-        const int off = ((h * 4 + c) ^ (r & 7)) << 4;
-        if (g.ablate & 16) continue;
-        *reinterpret_cast<float4*>(a_hi + off) = v[c];  // the tensor core ignores the low 13 mantissa bits
-        if (g.passes == 3) *reinterpret_cast<float4*>(a_lo + off) = lo;
-      }
-      fence_async_smem();
-      if (t == 0) NCF_TRACE(0, tr + 1);
-      tr += 2;
-      mbar_arrive_warp(&bars.full[s]);
-      if (++st_pi == panels) st_pi = 0;
-      if (++s == g.stages) { s = 0; ph ^= 1; }
-    };
-    if (g.gather) fetch_idx(0);
-    float4 buf[kDepth][4];
-#pragma unroll
-    for (int j = 0; j < kDepth; ++j)
-      if (j < n_iter) issue(buf[j]);
-    for (int64_t i0 = 0; i0 < n_iter; i0 += kDepth) {
-#pragma unroll
-      for (int j = 0; j < kDepth; ++j) {
-        const int64_t i = i0 + j;
-        if (i < n_iter) {
-          consume(buf[j]);
-          if (i + kDepth < n_iter) issue(buf[j]);
-        }
+        if (++pi == panels) pi = 0;
+        if (++s == g.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == kProducerWarps) {
@@ -574,6 +617,480 @@ umma_gemm_kernel(const __grid_constant__ TileParams p, const __grid_constant__ G
   if (EPI == EPI_PREDICT_TRAIN)
     for (int i = tid; i <= p.predict_size; i += kGemmThreads) atomicAdd(&p.gt[p.pw_off + i], bars.pg[i]);
   if (warp == kProducerWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+
+// ---- fused tower kernel ------------------------------------------------------------------------------
+// One 128-sample tile runs the whole tower forward and its backward-data pass without leaving the
+// SM: the A operand of every GEMM lives in tensor memory (gathered embedding rows for layer 0, the
+// previous epilogue's output for every other GEMM), so shared memory only carries the streamed
+// weight panels and the activations never go through shared memory at all.
+//   TMEM columns (f=32, L=3: widths 256,128,64,32):
+//     H[k] / Lo[k], k = 1..L (W[k] columns each): H[k] accumulates Z_k and then holds X_k (hi);
+//     Lo[k] holds X_k (lo), later accumulates dX_k and then holds dZ_k (hi) while dZ_k (lo) replaces
+//     X_k in H[k].  Layer 0's gathered panels go through a ring of 64-column stages laid over
+//     everything but H[1]; dX_0 accumulates in [2 W[1], 2 W[1] + W[0]).
+// Roles: warps 0-7 gather producers (two groups, alternate panels), 8-10 MMA issuers (one thread can
+// start a tcgen05.mma only every ~105 cycles and a tf32 MMA covers just K = 8, so the three products
+// of the split, hi*hi / lo*hi / hi*lo, are issued by three warps into the same accumulator, which the
+// preceding epilogue has zeroed), 11-18 epilogue (lane quarter x column half), 19 weight-panel loader.  Activations and deltas are also written to
+// the HBM scratch for the weight-gradient kernel.
+constexpr int kMaxGemms = 2 * NCF_MAX_LAYERS;
+constexpr int kRingMax = 6;
+constexpr int kBStages = 3;
+
+struct TowerGemm {
+  int kind;       // 0 forward layer k, 1 backward-data of layer k
+  int k, N, K;
+  int a_hi, a_lo; // TMEM columns of the A operand (-1: the gather ring)
+  int d_col;      // TMEM column of the accumulator
+  int n_total, row0;  // the weight image has n_total rows; this GEMM uses rows [row0, row0 + N)
+  int new_operand;    // the A operand was written by the epilogue of the previous GEMM (wait for it)
+  const float* img;
+};
+struct TowerArgs {
+  int passes, ng, ablate;
+  int ring_col, ring_stages;
+  int hcol[NCF_MAX_LAYERS + 1], lcol[NCF_MAX_LAYERS + 1];
+  TowerGemm gemm[kMaxGemms];
+};
+
+struct TowerBars {
+  uint64_t a_full[kRingMax], a_empty[kRingMax], b_full[kBStages], b_empty[kBStages];
+  uint64_t acc_ready[2], opnd_ready, tile_done;
+  uint32_t tmem_base;
+  float pg[2 * 128 + 4];
+};
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+        "r"(__float_as_uint(v[31])) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & kHiMask); }
+
+constexpr int kTowerThreads = 640;
+constexpr int kTowerEpiWarps = 8;
+constexpr int kTowerMmaWarp = 8;     // .. +2
+constexpr int kTowerEpiWarp0 = 11;
+constexpr int kTowerLoaderWarp = 19;
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ TowerArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ TowerBars bars;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = p.L;
+  const int64_t ntiles = (p.B + kTile - 1) / kTile;
+  const int64_t my_tiles = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int P0 = p.W[0] >> 5;               // gathered panels per tile
+  const uint32_t b_stage = 128u * 256u;     // largest panel: 128 rows x (hi + lo) x 128 B
+  uint8_t* land = smem + kBStages * b_stage;  // landing zone of the gathered rows: [panel][row][128 B], swizzled
+  const int NA = g.ring_stages;
+
+  if (tid == 0) {
+    const int nm = (g.passes == 3) ? 3 : 1;  // MMA-issuing warps, each commits for its own instructions
+    for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], 4); mbar_init(&bars.a_empty[s], nm); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], nm); }
+    mbar_init(&bars.acc_ready[0], nm);
+    mbar_init(&bars.acc_ready[1], nm);
+    mbar_init(&bars.opnd_ready, kTowerEpiWarps);
+    mbar_init(&bars.tile_done, kTowerEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 2 * 128 + 4; i += kTowerThreads) bars.pg[i] = 0.f;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp < 8) {
+    // ===== gather producers: thread = sample row (TMEM lane), group = parity of the panel ===================
+    // The rows of the NEXT tile are copied into the landing zone (cp.async, one commit group per panel)
+    // while this tile runs, so the gather latency is off the critical path: moving a panel into the
+    // TMEM ring is a shared-memory read of the thread's own row.
+    const int grp = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const int d = p.d;
+    const int own = P0 / 2;  // own panels per tile: grp, grp + 2, ...
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    int s = grp;            // ring stage of the next own panel (flat over tiles: P0 is even)
+    uint32_t ph = 0;
+    auto copy_panel = [&](int64_t tl, int pi, int64_t uu, int64_t ii) {
+      const bool ok = tl < my_tiles && uu >= 0 && uu < p.U && ii >= 0 && ii < p.I && !(g.ablate & 1);
+      const int c0 = pi * 32;
+      const float* src = p.eum;
+      if (ok) src = (c0 < d) ? p.eum + uu * d + c0 : p.eim + ii * d + (c0 - d);
+      uint8_t* dst = land + pi * (kTile * 128) + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cp_async16_zfill(dst + ((c ^ (r & 7)) << 4), src + c * 4, ok);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto row_idx = [&](int64_t tl, int64_t& uu, int64_t& ii) {
+      uu = -1;
+      ii = -1;
+      const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + r;
+      if (tl < my_tiles && row < p.B) {
+        uu = p.user[p.user_div > 0 ? row / p.user_div : row];
+        ii = p.item[row];
+      }
+    };
+    int64_t nu, nit;
+    row_idx(0, nu, nit);
+    for (int j = 0; j < own; ++j) copy_panel(0, grp + 2 * j, nu, nit);
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      row_idx(tl + 1, nu, nit);
+      // the ring overlays columns the previous tile's backward pass was still using
+      mbar_wait_warp(&bars.tile_done, (uint32_t)tl & 1);
+      for (int pi = grp; pi < P0; pi += 2) {
+        // pending groups: the rest of this tile's own panels, then the next tile's first ones
+        if (own == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (own == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        float cur[32];
+        const uint8_t* src = land + pi * (kTile * 128) + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(src + ((c ^ (r & 7)) << 4));
+          cur[4 * c] = x.x; cur[4 * c + 1] = x.y; cur[4 * c + 2] = x.z; cur[4 * c + 3] = x.w;
+        }
+        copy_panel(tl + 1, pi, nu, nit);  // refill the slot this thread has just read
+        mbar_wait_warp(&bars.a_empty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t col = lane_addr + g.ring_col + s * 64;
+        tc_st32(col, cur);
+        if (g.passes == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cur[j] = lo_of(cur[j]);
+          tc_st32(col + 32, cur);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive_warp(&bars.a_full[s]);
+        s += 2;
+        if (s >= NA) { s -= NA; ph ^= 1; }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == kTowerLoaderWarp) {
+    // ===== weight-panel loader ==================================================================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tl = 0; tl < my_tiles; ++tl)
+        for (int gi = 0; gi < g.ng; ++gi) {
+          const TowerGemm& G = g.gemm[gi];
+          const int panels = G.K >> 5;
+          const uint32_t bytes = (uint32_t)G.N * (g.passes == 3 ? 256u : 128u);
+          for (int pi = 0; pi < panels; ++pi) {
+            mbar_wait(&bars.b_empty[s], ph ^ 1);
+            const float* src = G.img + (int64_t)pi * 2 * G.n_total * 32 + (int64_t)G.row0 * 32;
+            uint8_t* dst = smem + (size_t)s * b_stage;
+            if (g.ablate & 2) {
+              mbar_arrive(&bars.b_full[s]);
+            } else if (G.N == G.n_total) {  // hi and lo of the panel are contiguous
+              mbar_expect_tx(&bars.b_full[s], bytes);
+              bulk_g2s(dst, src, bytes, &bars.b_full[s]);
+            } else {
+              mbar_expect_tx(&bars.b_full[s], bytes);
+              bulk_g2s(dst, src, (uint32_t)G.N * 128, &bars.b_full[s]);
+              if (g.passes == 3)
+                bulk_g2s(dst + G.N * 128, src + (int64_t)G.n_total * 32, (uint32_t)G.N * 128, &bars.b_full[s]);
+            }
+            if (++s == kBStages) { s = 0; ph ^= 1; }
+          }
+        }
+    }
+  } else if (warp >= kTowerMmaWarp && warp < kTowerMmaWarp + 3) {
+    // ===== MMA issuers: warp 8 hi*hi, warp 9 lo*hi, warp 10 hi*lo (accumulators are pre-zeroed) =======================
+    const int pass = warp - kTowerMmaWarp;
+    if (lane == 0 && (pass == 0 || g.passes == 3)) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, n_opnd = 0;
+      for (int64_t tl = 0; tl < my_tiles; ++tl)
+        for (int gi = 0; gi < g.ng; ++gi) {
+          const TowerGemm& G = g.gemm[gi];
+          const int panels = G.K >> 5;
+          const uint32_t idesc = make_idesc(kTile, G.N, 0, 0);
+          const uint32_t d_tmem = tmem + G.d_col;
+          if (G.new_operand) {  // operand written by the previous epilogue
+            mbar_wait(&bars.opnd_ready, n_opnd & 1);
+            ++n_opnd;
+            tc_fence_after();
+          }
+          if (pass == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi));
+          for (int pi = 0; pi < panels; ++pi) {
+            uint32_t a_hi, a_lo;
+            if (G.a_hi < 0) {
+              mbar_wait(&bars.a_full[sa], pha);
+              a_hi = tmem + g.ring_col + sa * 64;
+              a_lo = a_hi + 32;
+            } else {
+              a_hi = tmem + G.a_hi + pi * 32;
+              a_lo = tmem + G.a_lo + pi * 32;
+            }
+            mbar_wait(&bars.b_full[sb], phb);
+            tc_fence_after();
+            const uint32_t bhi = smem_u32(smem + (size_t)sb * b_stage);
+            // the k-step only moves the start-address field of the descriptor (32 B = 2 units of 16 B)
+            const uint64_t dbh0 = make_desc(bhi, 16, 1024, 2);
+            const uint64_t dbl0 = make_desc(bhi + (uint32_t)G.N * 128, 16, 1024, 2);
+            if (!(g.ablate & 4)) {
+              const uint32_t a_op = (pass == 1) ? a_lo : a_hi;
+              const uint64_t b_op = (pass == 2) ? dbl0 : dbh0;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc_mma_ts(d_tmem, a_op + ks * 8, b_op + 2 * ks, idesc, 1u);
+            }
+            if (G.a_hi < 0) {
+              tc_commit(&bars.a_empty[sa]);
+              if (++sa == NA) { sa = 0; pha ^= 1; }
+            }
+            tc_commit(&bars.b_empty[sb]);
+            if (++sb == kBStages) { sb = 0; phb ^= 1; }
+          }
+          tc_commit(&bars.acc_ready[gi & 1]);
+          if (pass == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi) + 1);
+        }
+    }
+  } else {
+    // ===== epilogue warps: lane quarter q, column half hf ============================================================
+    const int q = warp & 3, hf = (warp - kTowerEpiWarp0) >> 2;
+    const int f = p.f, dmlp = p.d;
+    const int mlp_off = (p.type == NCF_NEUMF) ? f : 0;
+    const bool has_gmf = p.type != NCF_MLP;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t n_acc[2] = {0, 0};
+    float v[32];
+    // every MMA accumulates: the accumulator of a GEMM is cleared by the epilogue that precedes it
+    auto zero_cols = [&](int col, int n) {
+      const int nchunk = n >> 5;
+      const int c_begin = (nchunk >= 2) ? hf * (nchunk / 2) * 32 : 0;
+      const int c_end = (nchunk >= 2) ? (hf + 1) * (nchunk / 2) * 32 : (hf == 0 ? n : 0);
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) tc_st32(lane_addr + col + c0, z);
+    };
+    zero_cols(g.gemm[0].d_col, g.gemm[0].N);
+    tc_wait_st();
+    tc_fence_before();
+    mbar_arrive_warp(&bars.tile_done);  // phase 0: "the tile before the first one is done"
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t row = (blockIdx.x + tl * gridDim.x) * kTile + q * 32 + lane;
+      const bool valid = row < p.B;
+      int64_t u = -1, it = -1;
+      bool bad = false;
+      if (valid) {
+        u = p.user[p.user_div > 0 ? row / p.user_div : row];
+        it = p.item[row];
+        if (u < 0 || u >= p.U || it < 0 || it >= p.I) { u = -1; bad = true; }
+      }
+      const bool ok = u >= 0;
+      float dl = 0.f;
+      for (int gi = 0; gi < g.ng; ++gi) {
+        const TowerGemm& G = g.gemm[gi];
+        mbar_wait_warp(&bars.acc_ready[gi & 1], n_acc[gi & 1] & 1);
+        ++n_acc[gi & 1];
+        if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi));
+        tc_fence_after();
+        const int N = G.N, k = G.k;
+        // column range of this warp: half of the accumulator, whole 32-column chunks
+        const int nchunk = N >> 5;
+        const int c_begin = (nchunk >= 2) ? hf * (nchunk / 2) * 32 : 0;
+        const int c_end = (nchunk >= 2) ? (hf + 1) * (nchunk / 2) * 32 : (hf == 0 ? N : 0);
+        if (g.ablate & 8) {
+          // nothing
+        } else if (G.kind == 0 && k + 1 < L) {
+          // ---- forward layer: X = relu(Z + b) -> scratch, TMEM hi (in place) and lo ------------------------
+          const int kk = k + 1;
+          const float* bias = p.b[k];
+          float* out = TRAIN ? p.act[kk] + row * (int64_t)N : nullptr;
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            tc_ld32(lane_addr + g.hcol[kk] + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + __ldg(&bias[c0 + j]), 0.f);
+            if (TRAIN && valid) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            tc_st32(lane_addr + g.hcol[kk] + c0, v);
+            if (g.passes == 3) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
+              tc_st32(lane_addr + g.lcol[kk] + c0, v);
+            }
+          }
+        } else if (G.kind == 0) {
+          // ---- last layer + predict layer (+ loss, predict grads, GMF scatter, delta_L) ---------------------
+          if (hf == 0) {
+            const float* bias = p.b[k];
+            float acc = 0.f;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+              tc_ld32(lane_addr + g.hcol[L] + c0, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                acc = fmaf(__ldg(&p.pw[mlp_off + c0 + j]), fmaxf(v[j] + __ldg(&bias[c0 + j]), 0.f), acc);
+            }
+            if (has_gmf && ok) {
+              const float* ru = p.eug + u * f;
+              const float* ri = p.eig + it * f;
+              for (int c = 0; c < f; c += 4) {
+                const float4 gu = ldg4(ru + c), gi4 = ldg4(ri + c), w = ldg4(p.pw + c);
+                acc = fmaf(w.x, gu.x * gi4.x, acc);
+                acc = fmaf(w.y, gu.y * gi4.y, acc);
+                acc = fmaf(w.z, gu.z * gi4.z, acc);
+                acc = fmaf(w.w, gu.w * gi4.w, acc);
+              }
+            }
+            float x = acc + __ldg(p.pb);
+            if (bad) x = __int_as_float(0x7fc00000);  // out-of-range index: NaN
+            if (valid && p.logits != nullptr) p.logits[row] = x;
+            if (TRAIN) {
+              float ls = 0.f;
+              if (ok && p.dlogit_in != nullptr) {
+                dl = p.dlogit_in[row];
+              } else if (ok) {
+                const float y = p.label[row];
+                const float e = expf(-fabsf(x));
+                const float bce = fmaxf(x, 0.f) - x * y + log1pf(e);
+                const float sig = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+                if (p.teacher != nullptr) {
+                  const float df = x - p.teacher[row];
+                  ls = p.alpha * bce + (1.f - p.alpha) * df * df;
+                  dl = (p.alpha * (sig - y) + (1.f - p.alpha) * 2.f * df) * p.invB;
+                } else {
+                  ls = bce;
+                  dl = (sig - y) * p.invB;
+                }
+              }
+              const float ls_w = warp_sum(ls), dl_w = warp_sum(dl);
+              if (lane == 0) {
+                if (p.loss_accum != nullptr) atomicAdd(p.loss_accum, (double)ls_w * (double)p.invB);
+                atomicAdd(&bars.pg[p.predict_size], dl_w);
+              }
+              float* dz = p.delta[L] + row * (int64_t)N;
+              for (int c0 = 0; c0 < N; c0 += 32) {
+                tc_ld32(lane_addr + g.hcol[L] + c0, v);
+                float z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float h = fmaxf(v[j] + __ldg(&bias[c0 + j]), 0.f);
+                  z[j] = (h > 0.f) ? dl * __ldg(&p.pw[mlp_off + c0 + j]) : 0.f;
+                  v[j] = dl * h;
+                }
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dz + c0 + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+                }
+                tc_st32(lane_addr + g.hcol[L] + c0, z);
+                const float s = warp_colsum32(v, lane);
+                atomicAdd(&bars.pg[mlp_off + c0 + lane], s);
+                if (g.passes == 3) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) z[j] = lo_of(z[j]);
+                  tc_st32(lane_addr + g.lcol[L] + c0, z);
+                }
+              }
+              if (has_gmf) {
+                for (int c0 = 0; c0 < f; c0 += 32) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    float4 gu = make_float4(0.f, 0.f, 0.f, 0.f), gi4 = gu;
+                    if (ok) {
+                      gu = ldg4(p.eug + u * f + c0 + j);
+                      gi4 = ldg4(p.eig + it * f + c0 + j);
+                      const float4 w = ldg4(p.pw + c0 + j);
+                      const float4 wd = make_float4(w.x * dl, w.y * dl, w.z * dl, w.w * dl);
+                      red_add4(p.gug + u * f + c0 + j, make_float4(wd.x * gi4.x, wd.y * gi4.y, wd.z * gi4.z, wd.w * gi4.w));
+                      red_add4(p.gig + it * f + c0 + j, make_float4(wd.x * gu.x, wd.y * gu.y, wd.z * gu.z, wd.w * gu.w));
+                    }
+                    v[j] = dl * (gu.x * gi4.x);
+                    v[j + 1] = dl * (gu.y * gi4.y);
+                    v[j + 2] = dl * (gu.z * gi4.z);
+                    v[j + 3] = dl * (gu.w * gi4.w);
+                  }
+                  const float s = warp_colsum32(v, lane);
+                  atomicAdd(&bars.pg[c0 + lane], s);
+                }
+              }
+            }
+          }
+        } else if (k > 0) {
+          // ---- backward data: dZ_k = dX_k * (X_k > 0) -> scratch, TMEM hi (in place) and lo (over X_k) --------
+          float* out = p.delta[k] + row * (int64_t)N;
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            float x[32];
+            tc_ld32(lane_addr + g.lcol[k] + c0, v);
+            tc_ld32(lane_addr + g.hcol[k] + c0, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (x[j] > 0.f) ? v[j] : 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            tc_st32(lane_addr + g.lcol[k] + c0, v);
+            if (g.passes == 3) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
+              tc_st32(lane_addr + g.hcol[k] + c0, v);
+            }
+          }
+        } else {
+          // ---- backward data of layer 0: scatter into the embedding-gradient rows -------------------------------
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            tc_ld32(lane_addr + G.d_col + c0, v);
+            if (ok) {
+              const int col = G.row0 + c0;
+              float* dst = (col < dmlp) ? p.gum + u * dmlp + col : p.gim + it * dmlp + (col - dmlp);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            }
+          }
+        }
+        // clear the accumulators of the GEMMs that start once this epilogue is done
+        if (gi + 1 == g.ng) {
+          zero_cols(g.gemm[0].d_col, g.gemm[0].N);
+        } else if (g.gemm[gi + 1].new_operand) {
+          for (int gj = gi + 1; gj < g.ng && (gj == gi + 1 || !g.gemm[gj].new_operand); ++gj)
+            zero_cols(g.gemm[gj].d_col, g.gemm[gj].N);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi) + 1);
+        if (gi + 1 == g.ng) mbar_arrive_warp(&bars.tile_done);
+        else if (g.gemm[gi + 1].new_operand) mbar_arrive_warp(&bars.opnd_ready);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (TRAIN)
+    for (int i = tid; i <= p.predict_size; i += kTowerThreads) atomicAdd(&p.gt[p.pw_off + i], bars.pg[i]);
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 // ---- weight-gradient kernel -----------------------------------------------------------------------------
@@ -957,6 +1474,67 @@ int tower_forward(TileParams& p, int passes, bool train, cudaStream_t st) {
   return NCF_OK;
 }
 
+// The fused kernel needs the whole tile's operand chain in the 512 TMEM columns.
+bool tower_fused_ok(const TileParams& p) {
+  const char* off = getenv("NCF_UMMA_FUSED");
+  if (off != nullptr && off[0] == '0') return false;
+  if (p.W[0] > 256 || p.W[p.L] < 32) return false;
+  int cols = 0;
+  for (int k = 1; k <= p.L; ++k) cols += 2 * p.W[k];
+  return cols <= 512 && 2 * p.W[1] + p.W[0] <= 512;
+}
+
+template <bool TRAIN>
+int launch_tower(const TileParams& p, int passes, cudaStream_t st) {
+  TowerArgs g{};
+  g.passes = passes;
+  if (const char* ab = getenv("NCF_UMMA_ABLATE")) g.ablate = atoi(ab);
+  int col = 0;
+  for (int k = 1; k <= p.L; ++k) {
+    g.hcol[k] = col;
+    col += p.W[k];
+    g.lcol[k] = col;
+    col += p.W[k];
+  }
+  g.ring_col = p.W[1];
+  g.ring_stages = std::min(kRingMax, (512 - p.W[1]) / 64);
+  for (int k = 0; k < p.L; ++k)
+    g.gemm[g.ng++] = TowerGemm{0, k, p.W[k + 1], p.W[k], k == 0 ? -1 : g.hcol[k], k == 0 ? -1 : g.lcol[k],
+                               g.hcol[k + 1], p.W[k + 1], 0, k > 0, p.wsplit_f[k]};
+  if (TRAIN)
+    for (int k = p.L - 1; k >= 0; --k) {
+      const bool top = (k + 1 == p.L);
+      const int a_hi = top ? g.hcol[p.L] : g.lcol[k + 1], a_lo = top ? g.lcol[p.L] : g.hcol[k + 1];
+      // accumulators are at most 128 columns wide (weight panels of <= 32 KB): wider outputs in blocks
+      for (int n0 = 0; n0 < p.W[k]; n0 += 128) {
+        const int N = std::min(128, p.W[k] - n0);
+        g.gemm[g.ng++] = TowerGemm{1, k, N, p.W[k + 1], a_hi, a_lo, (k >= 1 ? g.lcol[k] : 2 * p.W[1]) + n0,
+                                   p.W[k], n0, n0 == 0, p.wsplit_b[k]};
+      }
+    }
+  const size_t smem = (size_t)kBStages * 128 * 256 + (size_t)(p.W[0] / 32) * kTile * 128 + 1024;
+  auto kern = umma_tower_kernel<TRAIN>;
+  NCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (p.B + kTile - 1) / kTile;
+  int64_t grid = ncf::num_sms();
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kTowerThreads, smem, st>>>(p, g);
+  NCF_LAUNCH_CHECK("umma_tower_kernel");
+#ifdef NCF_UMMA_TRACE
+  if (getenv("NCF_UMMA_TRACE_TOWER")) {
+    cudaStreamSynchronize(st);
+    static long long h[3][128];
+    cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
+    const long long t0 = h[1][0];
+    for (int i = 0; i < 2 * g.ng; ++i)
+      fprintf(stderr, "[ttrace] tile %d gemm %d (kind %d k %d N %3d K %3d): mma start %7lld issued %7lld | epi acc-ok %7lld done %7lld\n",
+              i / g.ng, i % g.ng, g.gemm[i % g.ng].kind, g.gemm[i % g.ng].k, g.gemm[i % g.ng].N, g.gemm[i % g.ng].K,
+              h[1][2 * i] - t0, h[1][2 * i + 1] - t0, h[2][2 * i] - t0, h[2][2 * i + 1] - t0);
+  }
+#endif
+  return NCF_OK;
+}
+
 }  // namespace
 
 namespace ncf {
@@ -1016,6 +1594,11 @@ static float* carve(TileParams& p, float* ws, int64_t B, bool train, cudaStream_
 int launch_umma_forward(TileParams& p, int passes, float* ws, cudaStream_t st) {
   int rc;
   const int64_t B = p.B;
+  if (tower_fused_ok(p)) {
+    carve(p, ws, 0, false, st, &rc);
+    if (rc != NCF_OK) return rc;
+    return launch_tower<false>(p, passes, st);
+  }
   int64_t sub = kForwardSub;
   if (p.user_div > 0) sub = std::max<int64_t>(1, sub / p.user_div) * p.user_div;
   carve(p, ws, std::min(B, sub), false, st, &rc);
@@ -1040,6 +1623,14 @@ int launch_umma_train(TileParams& p, int passes, float* ws, cudaStream_t st) {
   carve(p, ws, p.B, true, st, &rc);
   if (rc != NCF_OK) return rc;
   timer.mark("images");
+  if (tower_fused_ok(p)) {
+    rc = launch_tower<true>(p, passes, st);
+    if (rc != NCF_OK) return rc;
+    timer.mark("tower");
+    rc = launch_wgrad(p, passes, st);
+    timer.mark("wgrad");
+    return rc;
+  }
   rc = tower_forward(p, passes, true, st);
   if (rc != NCF_OK) return rc;
   for (int k = p.L - 1; k >= 0; --k) {

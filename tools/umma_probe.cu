@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   const bool a_mn = (mode == 1 || mode == 2 || mode == 3 || mode == 5);
   const bool b_mn = (mode == 1 || mode == 2 || mode == 4 || mode == 6);
   const bool swp = (mode == 2 || mode == 5 || mode == 6);
-  if (mode == 7 || mode == 10) {            // K-major, SWIZZLE_128B: rows = M/N, cols = K (one 32-column panel)
+  if (mode == 7 || mode == 10 || mode == 11) {            // K-major, SWIZZLE_128B: rows = M/N, cols = K (one 32-column panel)
     fill_swizzled(a_img, A, M, K, K, 0);
     fill_swizzled(b_img, B, N, K, K, 0);
   } else if (mode == 8 || mode == 9) {     // MN-major: rows = K, cols = M/N; 8: SWIZZLE_128B, 9: 128B_BASE32B
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // generic-proxy writes of the operand images must be visible to the async (tensor core) proxy
@@ -109,12 +109,30 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base;
+  if (mode == 11) {
+    // A operand in tensor memory: thread = row m (lane 32*warp + lane), element (m, k) at column 64 + k
+    const int row = warp * 32 + lane;
+    uint32_t r[32];
+    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(A[row * K + k]);
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 64;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
 
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc(M, N, a_mn || mode == 8 || mode == 9, b_mn || mode == 8 || mode == 9);
     for (int ks = 0; ks < K / 8; ++ks) {
       uint64_t da, db;
-      if (mode == 7 || mode == 10) {
+      if (mode == 7 || mode == 10 || mode == 11) {
         // K-major SW128: 8-row groups 1024 B apart (SBO); the k-step advances 32 B inside the 128-B row
         da = make_desc(smem_u32(a_img) + ks * 32, 16, 1024, 2);
         db = make_desc(smem_u32(b_img) + ks * 32, 16, 1024, 2);
@@ -135,6 +153,13 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
       else if (!swp) db = make_desc(smem_u32(b_img) + ks * (N / 4) * 128, (N / 4) * 128, 128);
       else db = make_desc(smem_u32(b_img) + ks * (N / 4) * 128, 128, (N / 4) * 128);
       const uint32_t acc = ks > 0;
+      if (mode == 11) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem), "r"(tmem + 64 + ks * 8), "l"(db), "r"(idesc), "r"(acc));
+        continue;
+      }
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
           "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -168,7 +193,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
 static float tf32_exact(float x) {  // keep 10 mantissa bits so the reference is exact
@@ -192,7 +217,7 @@ int main() {
   const size_t smem = sizeof(float) * (M * K + N * K);
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int rc = 0;
-  for (int mode = 0; mode < 11; ++mode) {
+  for (int mode = 0; mode < 12; ++mode) {
     // mode 10: operands carry 0.75 ulp(tf32) of extra low mantissa bits; the result equals the exact
     // one iff the tensor core TRUNCATES fp32 -> tf32 (round-to-nearest would move every operand up)
     std::vector<float> Alow(A), Blow(B);
