@@ -684,6 +684,37 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 }
 __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & kHiMask); }
 
+// Epilogue threads own one sample row each (TMEM lane), so a plain 16-byte store touches 32 cache
+// lines per instruction and the LSU serialises them.  Transposing 8x8 blocks of float4 inside groups
+// of 8 lanes (48 shuffles per 32 columns) lets 8 lanes write one full 128-byte line of a row instead:
+// on return, v[4i..4i+3] of lane l hold columns [4(l%8), 4(l%8)+4) of the row owned by lane (l & ~7) + i.
+__device__ __forceinline__ void quad8_transpose(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if ((i & o) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float send = upper ? v[4 * i + e] : v[4 * (i + o) + e];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+          if (upper) v[4 * i + e] = recv; else v[4 * (i + o) + e] = recv;
+        }
+      }
+    }
+  }
+}
+// this lane's columns [c0, c0 + 32) of its row -> dst[row][c0 ..], rows of the warp start at wrow0
+__device__ __forceinline__ void store_rows(float (&v)[32], float* dst, int64_t ld, int64_t wrow0, int64_t nrows, int c0, int lane) {
+  quad8_transpose(v, lane);
+  const int64_t r0 = wrow0 + (lane & ~7);
+  float* p0 = dst + r0 * ld + c0 + 4 * (lane & 7);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (r0 + i < nrows) *reinterpret_cast<float4*>(p0 + i * ld) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
 constexpr int kTowerThreads = 640;
 constexpr int kTowerEpiWarps = 8;
 constexpr int kTowerMmaWarp = 8;     // .. +2
@@ -765,6 +796,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
       mbar_wait_warp(&bars.tile_done, (uint32_t)tl & 1);
       for (int pi = grp; pi < P0; pi += 2) {
         // pending groups: the rest of this tile's own panels, then the next tile's first ones
+        if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2));
         if (own == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
         else if (own == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -776,7 +808,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           cur[4 * c] = x.x; cur[4 * c + 1] = x.y; cur[4 * c + 2] = x.z; cur[4 * c + 3] = x.w;
         }
         copy_panel(tl + 1, pi, nu, nit);  // refill the slot this thread has just read
+        if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 1);
         mbar_wait_warp(&bars.a_empty[s], ph ^ 1);
+        if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 2);
         tc_fence_after();
         const uint32_t col = lane_addr + g.ring_col + s * 64;
         tc_st32(col, cur);
@@ -787,6 +821,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         }
         tc_wait_st();
         tc_fence_before();
+        if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 3);
         mbar_arrive_warp(&bars.a_full[s]);
         s += 2;
         if (s >= NA) { s -= NA; ph ^= 1; }
@@ -844,6 +879,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
             uint32_t a_hi, a_lo;
             if (G.a_hi < 0) {
               mbar_wait(&bars.a_full[sa], pha);
+              if (pass == 0 && tl == 1) NCF_TRACE(2, 64 + 3 * pi);
               a_hi = tmem + g.ring_col + sa * 64;
               a_lo = a_hi + 32;
             } else {
@@ -851,6 +887,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               a_lo = tmem + G.a_lo + pi * 32;
             }
             mbar_wait(&bars.b_full[sb], phb);
+            if (pass == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 1);
             tc_fence_after();
             const uint32_t bhi = smem_u32(smem + (size_t)sb * b_stage);
             // the k-step only moves the start-address field of the descriptor (32 B = 2 units of 16 B)
@@ -867,6 +904,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               if (++sa == NA) { sa = 0; pha ^= 1; }
             }
             tc_commit(&bars.b_empty[sb]);
+            if (pass == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 2);
             if (++sb == kBStages) { sb = 0; phb ^= 1; }
           }
           tc_commit(&bars.acc_ready[gi & 1]);
@@ -925,23 +963,20 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           // ---- forward layer: X = relu(Z + b) -> scratch, TMEM hi (in place) and lo ------------------------
           const int kk = k + 1;
           const float* bias = p.b[k];
-          float* out = TRAIN ? p.act[kk] + row * (int64_t)N : nullptr;
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             tc_ld32(lane_addr + g.hcol[kk] + c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + __ldg(&bias[c0 + j]), 0.f);
-            if (TRAIN && valid) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
             tc_st32(lane_addr + g.hcol[kk] + c0, v);
             if (g.passes == 3) {
+              float lo[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
-              tc_st32(lane_addr + g.lcol[kk] + c0, v);
+              for (int j = 0; j < 32; ++j) lo[j] = lo_of(v[j]);
+              tc_st32(lane_addr + g.lcol[kk] + c0, lo);
             }
+            if (TRAIN) store_rows(v, p.act[kk], N, row - lane, p.B, c0, lane);
           }
+
         } else if (G.kind == 0) {
           // ---- last layer + predict layer (+ loss, predict grads, GMF scatter, delta_L) ---------------------
           if (hf == 0) {
@@ -990,7 +1025,6 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                 if (p.loss_accum != nullptr) atomicAdd(p.loss_accum, (double)ls_w * (double)p.invB);
                 atomicAdd(&bars.pg[p.predict_size], dl_w);
               }
-              float* dz = p.delta[L] + row * (int64_t)N;
               for (int c0 = 0; c0 < N; c0 += 32) {
                 tc_ld32(lane_addr + g.hcol[L] + c0, v);
                 float z[32];
@@ -1000,19 +1034,15 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                   z[j] = (h > 0.f) ? dl * __ldg(&p.pw[mlp_off + c0 + j]) : 0.f;
                   v[j] = dl * h;
                 }
-                if (valid) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dz + c0 + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
-                }
                 tc_st32(lane_addr + g.hcol[L] + c0, z);
                 const float s = warp_colsum32(v, lane);
                 atomicAdd(&bars.pg[mlp_off + c0 + lane], s);
                 if (g.passes == 3) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) z[j] = lo_of(z[j]);
-                  tc_st32(lane_addr + g.lcol[L] + c0, z);
+                  for (int j = 0; j < 32; ++j) v[j] = lo_of(z[j]);
+                  tc_st32(lane_addr + g.lcol[L] + c0, v);
                 }
+                store_rows(z, p.delta[L], N, row - lane, p.B, c0, lane);
               }
               if (has_gmf) {
                 for (int c0 = 0; c0 < f; c0 += 32) {
@@ -1040,34 +1070,33 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           }
         } else if (k > 0) {
           // ---- backward data: dZ_k = dX_k * (X_k > 0) -> scratch, TMEM hi (in place) and lo (over X_k) --------
-          float* out = p.delta[k] + row * (int64_t)N;
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             float x[32];
             tc_ld32(lane_addr + g.lcol[k] + c0, v);
             tc_ld32(lane_addr + g.hcol[k] + c0, x);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (x[j] > 0.f) ? v[j] : 0.f;
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
             tc_st32(lane_addr + g.lcol[k] + c0, v);
             if (g.passes == 3) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
-              tc_st32(lane_addr + g.hcol[k] + c0, v);
+              for (int j = 0; j < 32; ++j) x[j] = lo_of(v[j]);
+              tc_st32(lane_addr + g.hcol[k] + c0, x);
             }
+            store_rows(v, p.delta[k], N, row - lane, p.B, c0, lane);
           }
         } else {
           // ---- backward data of layer 0: scatter into the embedding-gradient rows -------------------------------
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             tc_ld32(lane_addr + G.d_col + c0, v);
-            if (ok) {
-              const int col = G.row0 + c0;
-              float* dst = (col < dmlp) ? p.gum + u * dmlp + col : p.gim + it * dmlp + (col - dmlp);
+            quad8_transpose(v, lane);  // 8 lanes now hold one full 128-byte line of a row
+            const int col = G.row0 + c0;
+            const bool to_user = col < dmlp;
+            const int64_t my_idx = ok ? (to_user ? u : it) : -1;
+            float* tab = (to_user ? p.gum + col : p.gim + (col - dmlp)) + 4 * (lane & 7);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int i = 0; i < 8; ++i) {
+              const int64_t idx = __shfl_sync(0xffffffffu, my_idx, (lane & ~7) + i);
+              if (idx >= 0) red_add4(tab + idx * dmlp, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
           }
         }
@@ -1101,7 +1130,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
 // for its share of the batch; the accumulator stays in TMEM until the CTA's last chunk.
 constexpr int kWgProducerWarps = 8;
 constexpr int kWgProducers = kWgProducerWarps * 32;
-constexpr int kWgradThreads = kWgProducers + 32;  // + the MMA warp
+constexpr int kWgradThreads = kWgProducers + 96;  // + three MMA-issuing warps (one per product of the split)
 
 struct WgradBars {
   uint64_t full[2], empty[2], acc_full;
@@ -1134,8 +1163,9 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
   const int64_t my_chunks = (local < nchunks) ? (nchunks - local + job.nctas - 1) / job.nctas : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars.full[s], kWgProducerWarps); mbar_init(&bars.empty[s], 1); }
-    mbar_init(&bars.acc_full, 1);
+    const int nm = (g.passes == 3) ? 3 : 1;
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars.full[s], kWgProducerWarps); mbar_init(&bars.empty[s], nm); }
+    mbar_init(&bars.acc_full, nm);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 128) bars.db[tid] = 0.f;
@@ -1147,6 +1177,18 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
+  // every MMA accumulates (three warps issue into the same block): clear the accumulator first
+  if (warp < kWgProducerWarps) {
+    float z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = 0.f;
+    for (int c0 = (warp >> 2) * 128; c0 < (warp >> 2) * 128 + 128; c0 += 32)
+      tc_st32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, z);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp < kWgProducerWarps) {
     // Producers: every thread copies its 16-byte pieces of the chunk global -> shared with cp.async
@@ -1177,9 +1219,12 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         idxv[i] = (i < nbp && ci < my_chunks && row < p.B) ? idx_src[row] : -1;
       }
     };
-    auto issue = [&](int64_t ci) {
+    // blocking == false: copy only if the stage is already free (returns whether it did), so that a
+    // busy stage never holds back the hand-off of the chunk the MMA warps are waiting for
+    auto issue = [&](int64_t ci, bool blocking) -> bool {
       const int s = (int)(ci & 1);
-      mbar_wait_warp(&bars.empty[s], (uint32_t)((ci >> 1) & 1) ^ 1);
+      if (blocking) mbar_wait_warp(&bars.empty[s], (uint32_t)((ci >> 1) & 1) ^ 1);
+      else if (!mbar_test_warp(&bars.empty[s], (uint32_t)((ci >> 1) & 1) ^ 1)) return false;
       if (t == 0) NCF_TRACE(0, 2 * (int)ci);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       const int64_t row0 = (local + ci * job.nctas) * S;
@@ -1211,6 +1256,7 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (k == 0) issue_idx(ci + 1);
+      return true;
     };
     auto consume = [&](int64_t ci, bool more_pending) {
       const int s = (int)(ci & 1);
@@ -1247,11 +1293,12 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
       mbar_arrive_warp(&bars.full[s]);
     };
     if (k == 0) issue_idx(0);
-    if (my_chunks > 0) issue(0);
+    if (my_chunks > 0) issue(0, true);
     for (int64_t ci = 0; ci < my_chunks; ++ci) {
       const bool more = ci + 1 < my_chunks;
-      if (more) issue(ci + 1);
-      consume(ci, more);
+      const bool early = more && issue(ci + 1, false);
+      consume(ci, early);
+      if (more && !early) issue(ci + 1, true);
     }
     // bias gradient: column sums of delta (thread t always sees the same 4 columns)
     if (job.nb == 0) {
@@ -1278,28 +1325,22 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         }
       }
     }
-  } else if (lane == 0) {
+  } else if (lane == 0 && (warp == kWgProducerWarps || g.passes == 3)) {
+    const int pass = warp - kWgProducerWarps;  // 0 hi*hi, 1 lo*hi, 2 hi*lo
     const uint32_t idesc = make_idesc(128, NB, 1, 1);
     for (int64_t ci = 0; ci < my_chunks; ++ci) {
       const int s = (int)(ci & 1);
       mbar_wait(&bars.full[s], (uint32_t)(ci >> 1) & 1);
-      NCF_TRACE(1, 2 * (int)ci);
+      if (pass == 0) NCF_TRACE(1, 2 * (int)ci);
       tc_fence_after();
       const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t ahi = base, alo = base + a_img, bhi = base + 2 * a_img, blo = bhi + b_img;
-      for (int ks = 0; ks < ((g.ablate & 128) ? 0 : S / 8); ++ks) {
-        const uint64_t dah = make_desc(ahi + ks * 1024, S * 128, 512, 1);
-        const uint64_t dbh = make_desc(bhi + ks * 1024, S * 128, 512, 1);
-        tc_mma(tmem, dah, dbh, idesc, (ci > 0 || ks > 0) ? 1u : 0u);
-        if (g.passes == 3) {
-          const uint64_t dal = make_desc(alo + ks * 1024, S * 128, 512, 1);
-          const uint64_t dbl = make_desc(blo + ks * 1024, S * 128, 512, 1);
-          tc_mma(tmem, dal, dbh, idesc, 1u);
-          tc_mma(tmem, dah, dbl, idesc, 1u);
-        }
-      }
+      // the k-step (8 sample rows = 1024 B) only moves the start-address field: +64 units of 16 B
+      const uint64_t da0 = make_desc(pass == 1 ? alo : ahi, S * 128, 512, 1);
+      const uint64_t db0 = make_desc(pass == 2 ? blo : bhi, S * 128, 512, 1);
+      for (int ks = 0; ks < ((g.ablate & 128) ? 0 : S / 8); ++ks) tc_mma(tmem, da0 + 64 * ks, db0 + 64 * ks, idesc, 1u);
       tc_commit(&bars.empty[s]);
-      NCF_TRACE(1, 2 * (int)ci + 1);
+      if (pass == 0) NCF_TRACE(1, 2 * (int)ci + 1);
     }
     if (my_chunks > 0) tc_commit(&bars.acc_full);
   }
@@ -1526,6 +1567,12 @@ int launch_tower(const TileParams& p, int passes, cudaStream_t st) {
     static long long h[3][128];
     cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
     const long long t0 = h[1][0];
+    for (int i = 0; i < 4; ++i)
+      fprintf(stderr, "[ptrace] own panel %d: start %7lld landed+read %7lld ring-free %7lld stored %7lld\n", i, h[0][4 * i] - t0,
+              h[0][4 * i + 1] - t0, h[0][4 * i + 2] - t0, h[0][4 * i + 3] - t0);
+    for (int i = 0; i < 8; ++i)
+      fprintf(stderr, "[mtrace] panel %d: a_full %7lld b_full %7lld committed %7lld\n", i, h[2][64 + 3 * i] - t0,
+              h[2][64 + 3 * i + 1] - t0, h[2][64 + 3 * i + 2] - t0);
     for (int i = 0; i < 2 * g.ng; ++i)
       fprintf(stderr, "[ttrace] tile %d gemm %d (kind %d k %d N %3d K %3d): mma start %7lld issued %7lld | epi acc-ok %7lld done %7lld\n",
               i / g.ng, i % g.ng, g.gemm[i % g.ng].kind, g.gemm[i % g.ng].k, g.gemm[i % g.ng].N, g.gemm[i % g.ng].K,
