@@ -656,9 +656,10 @@ struct TowerArgs {
 
 struct TowerBars {
   uint64_t a_full[kRingMax], a_empty[kRingMax], b_full[kBStages], b_empty[kBStages];
-  uint64_t acc_ready[2], opnd_ready, tile_done;
+  uint64_t acc_ready[2], opnd_ready, tile_done, dl_ready;
   uint32_t tmem_base;
-  float pg[2 * 128 + 4];
+  float pg[2 * 64 + 8];  // predict-layer gradient of this CTA (the fused kernel serves f <= 64)
+  float xch[kTile];      // hand-off between the two epilogue warps of a lane quarter: GMF logit, then dlogit
 };
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
@@ -744,9 +745,10 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     mbar_init(&bars.acc_ready[1], nm);
     mbar_init(&bars.opnd_ready, kTowerEpiWarps);
     mbar_init(&bars.tile_done, kTowerEpiWarps);
+    mbar_init(&bars.dl_ready, kTowerEpiWarps / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 2 * 128 + 4; i += kTowerThreads) bars.pg[i] = 0.f;
+  for (int i = tid; i < 2 * 64 + 8; i += kTowerThreads) bars.pg[i] = 0.f;
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -790,7 +792,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     int64_t nu, nit;
     row_idx(0, nu, nit);
     for (int j = 0; j < own; ++j) copy_panel(0, grp + 2 * j, nu, nit);
+    const int f = p.f;
+    const bool has_gmf = p.type != NCF_MLP;
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t u = nu, it = nit;  // this tile's row
+      const bool ok = u >= 0 && u < p.U && it >= 0 && it < p.I;
       row_idx(tl + 1, nu, nit);
       // the ring overlays columns the previous tile's backward pass was still using
       mbar_wait_warp(&bars.tile_done, (uint32_t)tl & 1);
@@ -825,6 +831,48 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         mbar_arrive_warp(&bars.a_full[s]);
         s += 2;
         if (s >= NA) { s -= NA; ph ^= 1; }
+      }
+      // GMF branch backward (group 0, idle until the next tile): wait for this tile's dloss/dlogit
+      if (TRAIN && grp == 0) {
+        mbar_wait_warp(&bars.dl_ready, (uint32_t)tl & 1);
+        const float dl = bars.xch[r];
+        float v[32];
+              if (has_gmf) {
+                for (int c0 = 0; c0 < f; c0 += 32) {
+                  float gu_[32], gi_[32];
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    float4 gu = make_float4(0.f, 0.f, 0.f, 0.f), gi4 = gu;
+                    if (ok) {
+                      gu = ldg4(p.eug + u * f + c0 + j);
+                      gi4 = ldg4(p.eig + it * f + c0 + j);
+                    }
+                    const float4 w = ldg4(p.pw + c0 + j);
+                    const float4 wd = make_float4(w.x * dl, w.y * dl, w.z * dl, w.w * dl);
+                    v[j] = dl * (gu.x * gi4.x);
+                    v[j + 1] = dl * (gu.y * gi4.y);
+                    v[j + 2] = dl * (gu.z * gi4.z);
+                    v[j + 3] = dl * (gu.w * gi4.w);
+                    gu_[j] = wd.x * gi4.x; gu_[j + 1] = wd.y * gi4.y; gu_[j + 2] = wd.z * gi4.z; gu_[j + 3] = wd.w * gi4.w;
+                    gi_[j] = wd.x * gu.x; gi_[j + 1] = wd.y * gu.y; gi_[j + 2] = wd.z * gu.z; gi_[j + 3] = wd.w * gu.w;
+                  }
+                  const float s = warp_colsum32(v, lane);
+                  atomicAdd(&bars.pg[c0 + lane], s);
+                  // full-line REDs: 8 lanes per embedding-gradient row
+                  quad8_transpose(gu_, lane);
+                  quad8_transpose(gi_, lane);
+                  const int64_t mu = ok ? u : -1, mi = ok ? it : -1;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int64_t ru = __shfl_sync(0xffffffffu, mu, (lane & ~7) + i);
+                    const int64_t ri = __shfl_sync(0xffffffffu, mi, (lane & ~7) + i);
+                    if (ru >= 0) {
+                      red_add4(p.gug + ru * f + c0 + 4 * (lane & 7), make_float4(gu_[4 * i], gu_[4 * i + 1], gu_[4 * i + 2], gu_[4 * i + 3]));
+                      red_add4(p.gig + ri * f + c0 + 4 * (lane & 7), make_float4(gi_[4 * i], gi_[4 * i + 1], gi_[4 * i + 2], gi_[4 * i + 3]));
+                    }
+                  }
+                }
+              }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -945,9 +993,31 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         if (u < 0 || u >= p.U || it < 0 || it >= p.I) { u = -1; bad = true; }
       }
       const bool ok = u >= 0;
-      float dl = 0.f;
+      float dl = 0.f, pre_label = 0.f, pre_teacher = 0.f;
       for (int gi = 0; gi < g.ng; ++gi) {
         const TowerGemm& G = g.gemm[gi];
+        if (G.kind == 0 && G.k + 1 == L) {
+          // while the last layer is still running: half 1 gathers the GMF rows and reduces the GMF part
+          // of the logit, half 0 fetches the label
+          if (hf == 1) {
+            float gd = 0.f;
+            if (has_gmf && ok) {
+              const float* ru = p.eug + u * f;
+              const float* ri = p.eig + it * f;
+              for (int c = 0; c < f; c += 4) {
+                const float4 gu = ldg4(ru + c), gi4 = ldg4(ri + c), w = ldg4(p.pw + c);
+                gd = fmaf(w.x, gu.x * gi4.x, gd);
+                gd = fmaf(w.y, gu.y * gi4.y, gd);
+                gd = fmaf(w.z, gu.z * gi4.z, gd);
+                gd = fmaf(w.w, gu.w * gi4.w, gd);
+              }
+            }
+            bars.xch[q * 32 + lane] = gd;
+          } else if (TRAIN && ok && p.dlogit_in == nullptr) {
+            pre_label = p.label[row];
+            if (p.teacher != nullptr) pre_teacher = p.teacher[row];
+          }
+        }
         mbar_wait_warp(&bars.acc_ready[gi & 1], n_acc[gi & 1] & 1);
         ++n_acc[gi & 1];
         if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi));
@@ -979,6 +1049,10 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
 
         } else if (G.kind == 0) {
           // ---- last layer + predict layer (+ loss, predict grads, GMF scatter, delta_L) ---------------------
+          // The two warps of a lane quarter split the work: half 0 owns the tower side (logit, loss,
+          // delta_L), half 1 the GMF branch (its partial logit was computed before the accumulator was
+          // ready; the GMF gradients once half 0 has published dloss/dlogit).
+          const int trow = q * 32 + lane;
           if (hf == 0) {
             const float* bias = p.b[k];
             float acc = 0.f;
@@ -988,18 +1062,8 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               for (int j = 0; j < 32; ++j)
                 acc = fmaf(__ldg(&p.pw[mlp_off + c0 + j]), fmaxf(v[j] + __ldg(&bias[c0 + j]), 0.f), acc);
             }
-            if (has_gmf && ok) {
-              const float* ru = p.eug + u * f;
-              const float* ri = p.eig + it * f;
-              for (int c = 0; c < f; c += 4) {
-                const float4 gu = ldg4(ru + c), gi4 = ldg4(ri + c), w = ldg4(p.pw + c);
-                acc = fmaf(w.x, gu.x * gi4.x, acc);
-                acc = fmaf(w.y, gu.y * gi4.y, acc);
-                acc = fmaf(w.z, gu.z * gi4.z, acc);
-                acc = fmaf(w.w, gu.w * gi4.w, acc);
-              }
-            }
-            float x = acc + __ldg(p.pb);
+            named_bar(1 + q, 64);  // half 1 has written the GMF partial logit
+            float x = acc + bars.xch[trow] + __ldg(p.pb);
             if (bad) x = __int_as_float(0x7fc00000);  // out-of-range index: NaN
             if (valid && p.logits != nullptr) p.logits[row] = x;
             if (TRAIN) {
@@ -1007,12 +1071,12 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               if (ok && p.dlogit_in != nullptr) {
                 dl = p.dlogit_in[row];
               } else if (ok) {
-                const float y = p.label[row];
+                const float y = pre_label;
                 const float e = expf(-fabsf(x));
                 const float bce = fmaxf(x, 0.f) - x * y + log1pf(e);
                 const float sig = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
                 if (p.teacher != nullptr) {
-                  const float df = x - p.teacher[row];
+                  const float df = x - pre_teacher;
                   ls = p.alpha * bce + (1.f - p.alpha) * df * df;
                   dl = (p.alpha * (sig - y) + (1.f - p.alpha) * 2.f * df) * p.invB;
                 } else {
@@ -1020,6 +1084,8 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                   dl = (sig - y) * p.invB;
                 }
               }
+              bars.xch[trow] = dl;
+              mbar_arrive_warp(&bars.dl_ready);  // the GMF-branch gradients are the idle gather warps' job
               const float ls_w = warp_sum(ls), dl_w = warp_sum(dl);
               if (lane == 0) {
                 if (p.loss_accum != nullptr) atomicAdd(p.loss_accum, (double)ls_w * (double)p.invB);
@@ -1044,29 +1110,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                 }
                 store_rows(z, p.delta[L], N, row - lane, p.B, c0, lane);
               }
-              if (has_gmf) {
-                for (int c0 = 0; c0 < f; c0 += 32) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    float4 gu = make_float4(0.f, 0.f, 0.f, 0.f), gi4 = gu;
-                    if (ok) {
-                      gu = ldg4(p.eug + u * f + c0 + j);
-                      gi4 = ldg4(p.eig + it * f + c0 + j);
-                      const float4 w = ldg4(p.pw + c0 + j);
-                      const float4 wd = make_float4(w.x * dl, w.y * dl, w.z * dl, w.w * dl);
-                      red_add4(p.gug + u * f + c0 + j, make_float4(wd.x * gi4.x, wd.y * gi4.y, wd.z * gi4.z, wd.w * gi4.w));
-                      red_add4(p.gig + it * f + c0 + j, make_float4(wd.x * gu.x, wd.y * gu.y, wd.z * gu.z, wd.w * gu.w));
-                    }
-                    v[j] = dl * (gu.x * gi4.x);
-                    v[j + 1] = dl * (gu.y * gi4.y);
-                    v[j + 2] = dl * (gu.z * gi4.z);
-                    v[j + 3] = dl * (gu.w * gi4.w);
-                  }
-                  const float s = warp_colsum32(v, lane);
-                  atomicAdd(&bars.pg[c0 + lane], s);
-                }
-              }
             }
+          } else {
+            named_bar(1 + q, 64);
           }
         } else if (k > 0) {
           // ---- backward data: dZ_k = dX_k * (X_k > 0) -> scratch, TMEM hi (in place) and lo (over X_k) --------
@@ -1519,7 +1565,7 @@ int tower_forward(TileParams& p, int passes, bool train, cudaStream_t st) {
 bool tower_fused_ok(const TileParams& p) {
   const char* off = getenv("NCF_UMMA_FUSED");
   if (off != nullptr && off[0] == '0') return false;
-  if (p.W[0] > 256 || p.W[p.L] < 32) return false;
+  if (p.W[0] > 256 || p.W[p.L] < 32 || p.f > 64) return false;
   int cols = 0;
   for (int k = 1; k <= p.L; ++k) cols += 2 * p.W[k];
   return cols <= 512 && 2 * p.W[1] + p.W[0] <= 512;
@@ -1633,7 +1679,7 @@ static float* carve(TileParams& p, float* ws, int64_t B, bool train, cudaStream_
   for (int k = 1; k < p.L; ++k) { p.act[k] = ws; ws += B * p.W[k]; }
   if (train)
     for (int k = 1; k <= p.L; ++k) { p.delta[k] = ws; ws += B * p.W[k]; }
-  umma_weight_images_kernel<<<dim3(16, 2 * p.L), 256, 0, st>>>(p);
+  umma_weight_images_kernel<<<dim3(64, 2 * p.L), 256, 0, st>>>(p);
   *rc = check_cuda(cudaGetLastError(), "umma_weight_images_kernel");
   return ws;
 }
