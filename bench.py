@@ -284,6 +284,8 @@ def run_ours(args):
     # mark, catch-up, weight split, fused tile, row Adam, tower Adam, finalize; the row-sharded step adds
     # bucket count/scan/place, a second mark, 2 gathers, 2 permutes and 2 scatter-adds (NCCL kernels not counted)
     launches_per_step = 17 if sharded is not None else 7
+    if B >= 8192 and f >= 32:   # tcgen05 path: weight images + tower + wgrad instead of split + fused tile
+        launches_per_step += 1
 
     # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
     phases = None
@@ -303,6 +305,26 @@ def run_ours(args):
         torch.cuda.synchronize()
         phases = {n: sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(K)) / K
                   for j, n in enumerate(names)}
+        # per-kernel times inside ncf_train_step_grads (CUDA events recorded by the library between
+        # its launches; profiling mode synchronises after each step, so outside the timed region)
+        import ctypes as C
+        from ncf_b200 import _lib
+        lib = _lib.load()
+        kernel_ms = {}
+        lib.ncf_profile_enable(1)
+        for k in range(K):
+            u, i, y = bu[sl(W + k)], bi[sl(W + k)], bl[sl(W + k)]
+            ops.adam_prepare(ts._m, ts._g, ts._s, u, i, ts.lr)
+            ops.train_step_grads(ts._m, ts._g, u, i, y, None, 1.0, ts.loss_accum, ts.workspace)
+            ops.adam_step(ts._m, ts._g, ts._s, ts.lr)
+            ms = (C.c_float * 16)()
+            nm = C.create_string_buffer(16 * 32)
+            n = lib.ncf_profile_read(ms, nm, 16, 32)
+            for j in range(n):
+                key = nm.raw[j * 32:(j + 1) * 32].split(b"\0")[0].decode()
+                kernel_ms[key] = kernel_ms.get(key, 0.0) + ms[j] / K
+        lib.ncf_profile_enable(0)
+        tile_path = {0: "none", 1: "generic", 2: "mma.sync", 3: "tcgen05"}[lib.ncf_last_tile_path()]
 
     # ---- end to end: host buffers, H2D + D2H inside the timed region -----------------------------------
     hu = bu.cpu().pin_memory(); hi = bi.cpu().pin_memory(); hl = bl.cpu().pin_memory()
@@ -358,7 +380,25 @@ def run_ours(args):
                    "achieved_gbs": alg_bytes[n] / (phases[n] * 1e-3) / 1e9,
                    "frac": alg_bytes[n] / (phases[n] * 1e-3) / 1e9 / hbm_peak} for n in phases}
         traffic = profile_traffic(dom)
-        if dom == "train_step_grads" and f >= 32:
+        if dom == "train_step_grads" and "tower" in kernel_ms:
+            # tcgen05 path: ncf_train_step_grads = weight images + umma_tower_kernel (forward and
+            # backward-data of the tower, fused with gather / loss / scatter) + umma_wgrad_kernel.
+            # The dominant kernel is the tower kernel: algorithmic FLOPs = 4 * MACs per sample.
+            flops = 4.0 * macs * B
+            achieved = flops / (kernel_ms["tower"] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "umma_tower_kernel (inside ncf_train_step_grads)",
+                        "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tensor_peak, "traffic": profile_traffic("umma_tower_kernel"),
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst). The kernel computes in fp32-parity "
+                                       "3xTF32 on tcgen05 (kind::tf32 runs at half the bf16 rate and every "
+                                       "algorithmic MAC costs 3 MMAs), so its own ceiling is peak / 6",
+                        "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0),
+                        "algorithmic_flops_per_launch": flops, "launch_ms": kernel_ms["tower"],
+                        "kernel_ms": kernel_ms,
+                        "wgrad": {"kernel": "umma_wgrad_kernel", "launch_ms": kernel_ms.get("wgrad"),
+                                  "achieved_tflops": 2.0 * macs * B / (kernel_ms["wgrad"] * 1e-3) / 1e12,
+                                  "traffic": profile_traffic("umma_wgrad_kernel")}}
+        elif dom == "train_step_grads" and f >= 32:
             # the fused fwd+bwd kernel is bound by the tensor pipe in fp32-parity (3xTF32) mode:
             # algorithmic FLOPs = 6 * MACs per sample (forward 2, dgrad 2, wgrad 2)
             flops = 6.0 * macs * B
@@ -374,6 +414,7 @@ def run_ours(args):
                         "unit": "GB/s", "frac": hbm[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes[dom], "launch_ms": phases[dom]}
         roofline["phase_ms"] = phases
+        roofline["tile_path"] = tile_path
         roofline["hbm_view"] = hbm
         roofline["hbm_peak_gbs"] = hbm_peak
         roofline["step_level"] = {"bytes_per_sample": 4 * R * 7 + 24,

@@ -114,6 +114,12 @@ const char* ncf_last_error(void);
 /* which tile-kernel family the calling thread's last forward / training call ran on:
  * 0 none yet, 1 generic (FMA), 2 mma.sync tensor path, 3 tcgen05/TMEM path (diagnostic; tests) */
 int ncf_last_tile_path(void);
+/* Measurement aid for bench.py: with profiling on, every training step on the tcgen05 path records
+ * the CUDA-event time of each of its launches (and synchronises the stream).  ncf_profile_read
+ * copies the last step's times (milliseconds) and, if names != NULL, their labels as cap strings of
+ * name_len bytes; returns the number of entries. */
+int ncf_profile_enable(int32_t on);
+int ncf_profile_read(float* ms, char* names, int32_t cap, int32_t name_len);
 /* number of floats in the flat tower buffer for this shape */
 int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num, int32_t num_layers);
 

@@ -1494,8 +1494,16 @@ int launch_wgrad(const TileParams& p, int passes, cudaStream_t st) {
   return NCF_OK;
 }
 
-// NCF_UMMA_TIMING=1: CUDA-event time of every launch of one training step, printed to stderr
-// (debugging aid; synchronises the stream).
+// Per-launch CUDA-event times of one training step on the tcgen05 path.  Enabled by
+// ncf_profile_enable(1) (results read back with ncf_profile_read) or NCF_UMMA_TIMING=1 (printed to
+// stderr).  Profiling synchronises the stream after every step: measurement aid, not for production.
+struct StepProfile {
+  int enabled = 0, n = 0;
+  float ms[16];
+  const char* name[16];
+};
+thread_local StepProfile g_profile;
+
 struct StepTimer {
   bool on;
   cudaStream_t st;
@@ -1503,7 +1511,7 @@ struct StepTimer {
   const char* name[32];
   int n = 0;
   static thread_local StepTimer* g_timer;
-  StepTimer(cudaStream_t s) : on(getenv("NCF_UMMA_TIMING") != nullptr), st(s) {
+  StepTimer(cudaStream_t s) : on(g_profile.enabled || getenv("NCF_UMMA_TIMING") != nullptr), st(s) {
     g_timer = this;
     mark("start");
   }
@@ -1517,10 +1525,16 @@ struct StepTimer {
     g_timer = nullptr;
     if (!on) return;
     cudaStreamSynchronize(st);
+    g_profile.n = 0;
     for (int i = 1; i < n; ++i) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      fprintf(stderr, "[umma] %-10s %8.1f us\n", name[i], ms * 1e3f);
+      if (g_profile.enabled && g_profile.n < 16) {
+        g_profile.ms[g_profile.n] = ms;
+        g_profile.name[g_profile.n++] = name[i];
+      } else {
+        fprintf(stderr, "[umma] %-10s %8.1f us\n", name[i], ms * 1e3f);
+      }
     }
     for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
   }
@@ -1751,3 +1765,18 @@ int launch_umma_train(TileParams& p, int passes, float* ws, cudaStream_t st) {
 }
 
 }  // namespace ncf
+
+extern "C" int ncf_profile_enable(int32_t on) {
+  g_profile.enabled = on;
+  g_profile.n = 0;
+  return NCF_OK;
+}
+
+extern "C" int ncf_profile_read(float* ms, char* names, int32_t cap, int32_t name_len) {
+  int n = g_profile.n < cap ? g_profile.n : cap;
+  for (int i = 0; i < n; ++i) {
+    ms[i] = g_profile.ms[i];
+    if (names != nullptr && name_len > 0) snprintf(names + (size_t)i * name_len, name_len, "%s", g_profile.name[i]);
+  }
+  return n;
+}
