@@ -136,6 +136,71 @@ class StepGraph:
             self.ts._dirty = True
 
 
+class HostFedTrainer:
+    """Training from HOST batches (pinned memory) with the copies off the critical path: two device
+    buffer sets, one captured step graph per set, and a copy stream that stages batch k+1 while
+    step k computes.  `prefetch(user, item, label)` stages a pinned host batch (asynchronous);
+    `step()` runs the oldest staged batch and returns its loss — the same per-step `loss.item()`
+    the reference loop reads (scripts/train_neumf.py:112-121).  Usage:
+
+        hf = HostFedTrainer(ts, batch); hf.prefetch(*b[0])
+        for k in range(n): hf.prefetch(*b[k + 1]); loss = hf.step()
+    """
+
+    def __init__(self, ts: FusedTrainStep, batch: int):
+        dev = ts.device
+        self.ts, self.batch = ts, batch
+        self.bufs = [(torch.empty(batch, dtype=torch.int64, device=dev),
+                      torch.empty(batch, dtype=torch.int64, device=dev),
+                      torch.empty(batch, dtype=torch.float32, device=dev)) for _ in range(2)]
+        for b in self.bufs:  # valid indices for the capture pass
+            b[0].zero_(); b[1].zero_(); b[2].zero_()
+        self.graphs = [ts.capture(*b, batch) for b in self.bufs]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.consumed:
+            e.record()
+        self.host_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self.n_staged = 0   # batches staged so far
+        self.n_run = 0      # batches trained so far
+
+    def prefetch(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor) -> None:
+        if self.n_staged - self.n_run >= 2:
+            raise _lib.NcfError("HostFedTrainer: two batches are already staged")
+        if user.numel() != self.batch:
+            raise _lib.NcfError("HostFedTrainer: batches must have the captured size")
+        j = self.n_staged & 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[j])
+            self.bufs[j][0].copy_(user, non_blocking=True)
+            self.bufs[j][1].copy_(item, non_blocking=True)
+            self.bufs[j][2].copy_(label, non_blocking=True)
+            self.copied[j].record(self.copy_stream)
+        self.n_staged += 1
+
+    def launch(self) -> None:
+        """Enqueues the step on the oldest staged batch and the read-back of its loss."""
+        if self.n_run >= self.n_staged:
+            raise _lib.NcfError("HostFedTrainer.step: no staged batch")
+        j = self.n_run & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.copied[j])
+        self.ts.loss_accum.zero_()
+        self.graphs[j].replay()
+        self.consumed[j].record()
+        self.host_loss.copy_(self.ts.loss_accum, non_blocking=True)
+        self.n_run += 1
+
+    def wait(self) -> float:
+        torch.cuda.current_stream().synchronize()
+        return float(self.host_loss[0])
+
+    def step(self) -> float:
+        self.launch()
+        return self.wait()
+
+
 class EpochStream:
     """On-device replacement of `NCFData.ng_sample()` + `DataLoader(shuffle=True)` (reference
     src/data/datasets.py:53-83, scripts/train_neumf.py:55,102): a CSR of the observed pairs, a

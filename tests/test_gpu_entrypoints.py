@@ -92,3 +92,40 @@ def test_tf32_tower_mode_within_stated_tolerance():
         fast = model(u, i)
     err = (fast - ref).abs().max().item() / ref.abs().max().item()
     assert 0 < err < 2e-3, err
+
+
+def test_host_fed_trainer_equals_eager_steps():
+    """HostFedTrainer (graph-captured steps fed from pinned host batches through a copy stream)
+    follows the same trajectory as eager FusedTrainStep.step on device batches."""
+    import copy
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep, HostFedTrainer
+    from tests.util import assert_close_adam
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    U, I, B, T = 300, 200, 512, 5
+    a = NCF(U, I, 8, 3, 0.0, "NeuMF-end").to(dev)
+    b = copy.deepcopy(a)
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randint(0, U, (B,), generator=g).pin_memory(), torch.randint(0, I, (B,), generator=g).pin_memory(),
+                (torch.rand(B, generator=g) < 0.3).float().pin_memory()) for _ in range(T)]
+    ta = FusedTrainStep(a, "adam", 1e-3, max_batch=B)
+    tb = FusedTrainStep(b, "adam", 1e-3, max_batch=B)
+    eager = []
+    for u, i, y in batches:
+        ta.step(u.to(dev), i.to(dev), y.to(dev))
+        eager.append(ta.pop_loss())
+    hf = HostFedTrainer(tb, B)
+    hf.prefetch(*batches[0])
+    fed = []
+    for k in range(T):
+        hf.launch()
+        if k + 1 < T:
+            hf.prefetch(*batches[k + 1])
+        fed.append(hf.wait())
+    for x, y in zip(eager, fed):
+        assert abs(x - y) <= 1e-6 * abs(x)
+    ta.flush(); tb.flush()
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert_close_adam(sb[k].cpu().numpy(), sa[k].cpu().numpy(), k)
