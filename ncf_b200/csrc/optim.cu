@@ -124,6 +124,84 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
   if (MODE != 1) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
   const int64_t total = n0 + n1;
   const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  // Fast path (NeuMF with rows of at most 128 floats, the bench shapes): a lane owns one float4 of the
+  // GMF row and one of the MLP row; all eight loads of a row are issued before anything is used, and
+  // the next row's list entry and last-step word are fetched while this row is in flight.
+  if (vec && q.has_gmf && q.has_mlp && q.f <= 128 && q.d <= 128) {
+    const bool lg = lane * 4 < q.f, lm = lane * 4 < q.d;
+    auto fetch = [&](int64_t e, int& side, int64_t& r, int32_t& last) {
+      side = e < n0 ? 0 : 1;
+      r = 0;
+      last = 0;
+      if (e < total) {
+        r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+        last = q.last[side][r];
+      }
+    };
+    int side, nside;
+    int64_t r, nr;
+    int32_t last, nlast;
+    fetch(wid, side, r, last);
+    for (int64_t e = wid; e < total; e += nw, side = nside, r = nr, last = nlast) {
+      fetch(e + nw, nside, nr, nlast);
+      int gap;
+      if (MODE == 0) {
+        gap = (last > 0) ? (int)(t - 1 - last) : 0;
+      } else {
+        if (last <= 0 || last >= t) continue;
+        gap = (int)(t - last);
+      }
+      const int64_t og = r * q.f + lane * 4, om = r * q.d + lane * 4;
+      float4 pg = make_float4(0, 0, 0, 0), mg = pg, vg = pg, gg = pg, pm = pg, mm = pg, vm = pg, gm = pg;
+      if (lg) {
+        pg = *reinterpret_cast<const float4*>(q.p_gmf[side] + og);
+        mg = *reinterpret_cast<const float4*>(q.m_gmf[side] + og);
+        vg = *reinterpret_cast<const float4*>(q.v_gmf[side] + og);
+        if (MODE == 0) gg = *reinterpret_cast<const float4*>(q.g_gmf[side] + og);
+      }
+      if (lm) {
+        pm = *reinterpret_cast<const float4*>(q.p_mlp[side] + om);
+        mm = *reinterpret_cast<const float4*>(q.m_mlp[side] + om);
+        vm = *reinterpret_cast<const float4*>(q.v_mlp[side] + om);
+        if (MODE == 0) gm = *reinterpret_cast<const float4*>(q.g_mlp[side] + om);
+      }
+      __syncwarp();
+      const int n = min(gap, kMaxReplay);
+      for (int j = lane; j < n; j += 32) {
+        const float s = (float)(last + 1 + j);
+        c1s[j] = bias_c1(q.c, s);
+        c2s[j] = bias_c2(q.c, s);
+      }
+      __syncwarp();
+      float* a[8] = {&pg.x, &mg.x, &vg.x, &gg.x, &pm.x, &mm.x, &vm.x, &gm.x};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        replay_zero_steps(a[0][k], a[1][k], a[2][k], gap, c1s, c2s, q.c);
+        replay_zero_steps(a[4][k], a[5][k], a[6][k], gap, c1s, c2s, q.c);
+        if (MODE == 0) {
+          adam_real_step(a[0][k], a[1][k], a[2][k], a[3][k], c1t, c2t, q.c);
+          adam_real_step(a[4][k], a[5][k], a[6][k], a[7][k], c1t, c2t, q.c);
+        }
+      }
+      if (lg) {
+        *reinterpret_cast<float4*>(q.p_gmf[side] + og) = pg;
+        *reinterpret_cast<float4*>(q.m_gmf[side] + og) = mg;
+        *reinterpret_cast<float4*>(q.v_gmf[side] + og) = vg;
+        if (MODE == 0) *reinterpret_cast<float4*>(q.g_gmf[side] + og) = make_float4(0, 0, 0, 0);
+      }
+      if (lm) {
+        *reinterpret_cast<float4*>(q.p_mlp[side] + om) = pm;
+        *reinterpret_cast<float4*>(q.m_mlp[side] + om) = mm;
+        *reinterpret_cast<float4*>(q.v_mlp[side] + om) = vm;
+        if (MODE == 0) *reinterpret_cast<float4*>(q.g_mlp[side] + om) = make_float4(0, 0, 0, 0);
+      }
+      if (lane == 0) {
+        q.last[side][r] = (int32_t)t;
+        if (MODE == 0) q.flag[side][r] = 0;
+      }
+    }
+    return;
+  }
   for (int64_t e = wid; e < total; e += nw) {
     const int side = e < n0 ? 0 : 1;
     const int64_t r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
