@@ -76,13 +76,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
+// NCF_MBAR_POLL: busy-poll with test_wait instead of the suspending try_wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     uint32_t done;
+#ifdef NCF_MBAR_POLL
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
     if (done) return;
   }
   __trap();
@@ -813,7 +820,6 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           const float4 x = *reinterpret_cast<const float4*>(src + ((c ^ (r & 7)) << 4));
           cur[4 * c] = x.x; cur[4 * c + 1] = x.y; cur[4 * c + 2] = x.z; cur[4 * c + 3] = x.w;
         }
-        copy_panel(tl + 1, pi, nu, nit);  // refill the slot this thread has just read
         if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 1);
         mbar_wait_warp(&bars.a_empty[s], ph ^ 1);
         if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 2);
@@ -829,6 +835,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         tc_fence_before();
         if (warp == 0 && lane == 0 && tl == 1) NCF_TRACE(0, 4 * (pi / 2) + 3);
         mbar_arrive_warp(&bars.a_full[s]);
+        // refill the slot this thread has just read with the next tile's row - after the hand-off:
+        // the copies would otherwise sit in front of it in the warp's memory-instruction queue
+        copy_panel(tl + 1, pi, nu, nit);
         s += 2;
         if (s >= NA) { s -= NA; ph ^= 1; }
       }
