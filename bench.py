@@ -9,13 +9,17 @@ negatives per positive), batch 65 536, Adam lr 1e-3.  It is the config the metri
 samples/s @1/2/4/8 B200" is quoted on and it fits one GPU; configs[1] (ML-1M shape, batch 256) is
 launch-latency-bound and is a parity-test case (`--workload ml1m` runs it).
 A "step" is one optimisation step on one batch: [catch-up of lagging rows] -> fused
-gather+forward+loss+backward -> sparse-row Adam.  Under torchrun (N>1) every rank runs the same
-per-GPU batch on its own replica (weak scaling).
+gather+forward+loss+backward (tcgen05 path at this batch size: weight images, umma_tower_kernel,
+umma_wgrad_kernel) -> sparse-row Adam.  Under torchrun (N>1) every rank runs the same per-GPU
+batch on its own replica (weak scaling); `--workload big` (BASELINE configs[4], 10M x 1M tables)
+row-shards the tables instead.
 
-The JSON line carries `value` (device-resident inputs), `e2e` (host buffers through the public
-API with H2D/D2H inside the timed region), `roofline` of the dominant kernel, `cpu_baseline`
-(the reference's CPU op sequence, oracle/torch_port.py, timed on this box's host cores) and the
-clocks seen during the timed region.  `--impl reference` times only that CPU port.
+The JSON line carries `value` (device-resident inputs), `e2e` (pinned host batches through the
+public API — ncf_b200.trainer.HostFedTrainer on one GPU — with every step's H2D copies and loss
+read-back inside the timed region), `roofline` of the dominant kernel (timed by CUDA events the
+library records between its launches), `cpu_baseline` (the reference's CPU op sequence,
+oracle/torch_port.py, timed on this box's host cores) and the clocks seen during the timed
+region.  `--impl reference` times only that CPU port.
 """
 from __future__ import annotations
 
