@@ -118,6 +118,11 @@ int ncf_last_tile_path(void);
  * the CUDA-event time of each of its launches (and synchronises the stream).  ncf_profile_read
  * copies the last step's times (milliseconds) and, if names != NULL, their labels as cap strings of
  * name_len bytes; returns the number of entries. */
+/* Data-parallel overlap: makes `stream` wait until the embedding-row gradients (g_user_*, g_item_*) of
+ * the calling thread's last ncf_train_step_grads / ncf_backward call are complete.  On the tcgen05
+ * path that is before the weight-gradient kernel has run, so an all-reduce of the row gradients on
+ * another stream overlaps with it; the tower gradients are complete when the call's stream is. */
+int ncf_wait_embedding_grads(void* stream);
 int ncf_profile_enable(int32_t on);
 int ncf_profile_read(float* ms, char* names, int32_t cap, int32_t name_len);
 /* number of floats in the flat tower buffer for this shape */

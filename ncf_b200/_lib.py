@@ -56,6 +56,7 @@ SIGNATURES = {
     "ncf_version": (C.c_int, []),
     "ncf_last_error": (C.c_char_p, []),
     "ncf_last_tile_path": (C.c_int, []),
+    "ncf_wait_embedding_grads": (C.c_int, [_vp]),
     "ncf_profile_enable": (C.c_int, [_i32]),
     "ncf_profile_read": (C.c_int, [_vp, _vp, _i32, _i32]),
     "ncf_tower_param_count": (_i64, [_i32, _i32, _i32]),

@@ -63,6 +63,21 @@ extern "C" const char* ncf_last_error(void) { return ncf::g_err; }
 
 extern "C" int ncf_last_tile_path(void) { return ncf::g_tile_path; }
 
+namespace ncf {
+static thread_local cudaEvent_t g_embed_event = nullptr;
+int mark_embedding_grads_done(cudaStream_t st) {
+  if (g_embed_event == nullptr) NCF_CUDA(cudaEventCreateWithFlags(&g_embed_event, cudaEventDisableTiming));
+  NCF_CUDA(cudaEventRecord(g_embed_event, st));
+  return NCF_OK;
+}
+}  // namespace ncf
+
+extern "C" int ncf_wait_embedding_grads(void* stream) {
+  NCF_REQUIRE(ncf::g_embed_event != nullptr, "ncf_wait_embedding_grads: no training step has run on this thread");
+  NCF_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ncf::g_embed_event, 0));
+  return NCF_OK;
+}
+
 extern "C" int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num,
                                          int32_t num_layers) {
   if (factor_num <= 0 || num_layers < 1 || num_layers > NCF_MAX_LAYERS) return -1;

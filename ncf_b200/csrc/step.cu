@@ -208,12 +208,16 @@ static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* use
   if (ncf::mma_tile_rows(p) != 0) {
     rc = ncf::mma_prepare_weights(p, (float*)workspace, (cudaStream_t)stream);
     if (rc != NCF_OK) return rc;
-    return ncf::launch_mma_train(p, ncf::tower_passes(m), (cudaStream_t)stream);
+    rc = ncf::launch_mma_train(p, ncf::tower_passes(m), (cudaStream_t)stream);
+    if (rc != NCF_OK) return rc;
+    return ncf::mark_embedding_grads_done((cudaStream_t)stream);
   }
   if (m->model_type != NCF_GMF) {
     float* ws = (float*)workspace;
     for (int k = 1; k < p.L; ++k) { p.act[k] = ws; ws += B * p.W[k]; }
     for (int k = 1; k <= p.L; ++k) { p.delta[k] = ws; ws += B * p.W[k]; }
   }
-  return ncf::launch_generic_train(p, (cudaStream_t)stream);
+  rc = ncf::launch_generic_train(p, (cudaStream_t)stream);
+  if (rc != NCF_OK) return rc;
+  return ncf::mark_embedding_grads_done((cudaStream_t)stream);
 }

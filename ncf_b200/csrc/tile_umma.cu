@@ -1746,6 +1746,7 @@ int launch_umma_train(TileParams& p, int passes, float* ws, cudaStream_t st) {
   if (tower_fused_ok(p)) {
     rc = launch_tower<true>(p, passes, st);
     if (rc != NCF_OK) return rc;
+    if ((rc = mark_embedding_grads_done(st)) != NCF_OK) return rc;
     timer.mark("tower");
     rc = launch_wgrad(p, passes, st);
     timer.mark("wgrad");
@@ -1772,6 +1773,7 @@ int launch_umma_train(TileParams& p, int passes, float* ws, cudaStream_t st) {
     if (rc != NCF_OK) return rc;
     timer.mark(k == 2 ? "dgrad2" : k == 1 ? "dgrad1" : k == 0 ? "dgrad0" : "dgrad");
   }
+  if ((rc = mark_embedding_grads_done(st)) != NCF_OK) return rc;
   rc = launch_wgrad(p, passes, st);
   timer.mark("wgrad");
   return rc;

@@ -37,10 +37,12 @@ def partition(n: int, world: int, rank: int):
 def gather_indices(user: torch.Tensor, item: torch.Tensor, world: int):
     """all_gather of the per-rank (user, item) index slices -> global [world * B] tensors."""
     B = user.numel()
-    both = torch.stack([user, item])                      # [2, B]
-    out = torch.empty(world, 2, B, dtype=user.dtype, device=user.device)
-    dist.all_gather_into_tensor(out.view(-1), both.view(-1))
-    return out[:, 0, :].reshape(-1).contiguous(), out[:, 1, :].reshape(-1).contiguous()
+    # two collectives straight into their rank-major outputs: no stack / slice copies around them
+    gu = torch.empty(world * B, dtype=user.dtype, device=user.device)
+    gi = torch.empty(world * B, dtype=item.dtype, device=item.device)
+    dist.all_gather_into_tensor(gu, user.contiguous())
+    dist.all_gather_into_tensor(gi, item.contiguous())
+    return gu, gi
 
 
 def average_(t: torch.Tensor, world: int):
@@ -72,6 +74,15 @@ class ReplicatedDataParallel:
         if check_replicas:
             for p in ts.model.parameters():  # start from rank 0's weights
                 dist.broadcast(p.data, src=0)
+        # the row gradients (all of the flat buffer but its tower tail) are reduced on a side stream as
+        # soon as they are complete, while the weight-gradient kernel is still running
+        # (measured on B200: +7 % at 4 GPUs, -5 % at 2, where the all-reduce is short and its CTAs mostly
+        # take issue slots from the weight-gradient kernel; NCF_DP_OVERLAP=0/1 overrides)
+        import os
+        want = os.environ.get("NCF_DP_OVERLAP")
+        overlap = (self.world >= 4) if want is None else (want == "1")
+        self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and overlap) else None
+        self.n_rows_flat = (ts.grads.g_tower.data_ptr() - ts.grads.flat.data_ptr()) // 4
 
     def step(self, user, item, label):
         ts = self.ts
@@ -81,7 +92,15 @@ class ReplicatedDataParallel:
         else:
             raise NotImplementedError("replicated DP is implemented for Adam")
         ops.train_step_grads(ts._m, ts._g, user, item, label, None, 1.0, ts.loss_accum, ts.workspace)
-        average_(ts.grads.flat, self.world)
+        flat = ts.grads.flat
+        if self.comm_stream is not None and dist.get_backend() == "nccl":
+            ops.wait_embedding_grads(self.comm_stream)
+            with torch.cuda.stream(self.comm_stream):
+                average_(flat[:self.n_rows_flat], self.world)
+            average_(flat[self.n_rows_flat:], self.world)      # tower gradients: after the wgrad kernel
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            average_(flat, self.world)
         ops.adam_step(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
         ts._dirty = True
         ts.num_steps += 1

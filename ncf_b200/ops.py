@@ -259,6 +259,13 @@ def train_step_grads(m: NcfModel, g: NcfGrads, user, item, label, teacher_logits
         "ncf_train_step_grads")
 
 
+def wait_embedding_grads(stream: torch.cuda.Stream) -> None:
+    """`stream` waits until the row gradients of the last train_step_grads call are complete (on the
+    tcgen05 path: before the weight-gradient kernel) — lets a data-parallel all-reduce of the row
+    gradients overlap with the rest of the step."""
+    check(_lib.load().ncf_wait_embedding_grads(C.c_void_p(stream.cuda_stream)), "ncf_wait_embedding_grads")
+
+
 def backward(m: NcfModel, g: NcfGrads, user, item, dlogit, workspace: torch.Tensor) -> None:
     """Backward from a caller-supplied dloss/dlogit (autograd compatibility path)."""
     check(_lib.load().ncf_backward(
