@@ -226,6 +226,13 @@ int ncf_adam_prepare(const NcfModel* m_host, const NcfGrads* g_host, const NcfAd
                      void* stream);
 int ncf_adam_step(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
                   NcfAdamHyper h, void* stream);
+/* The same optimiser step taken over EVERY row of the tables (the reference's dense Adam literally):
+ * rows without gradient take their zero-gradient step now instead of being replayed later.  Cheaper
+ * than list + catch-up + row gather once a step touches a large share of the rows (large batches,
+ * data-parallel global batches).  After it every row is current: the next step needs no
+ * ncf_adam_prepare (ncf_mark_rows is not needed for this entry either). */
+int ncf_adam_step_dense(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
+                        NcfAdamHyper h, void* stream);
 int ncf_adam_flush(const NcfModel* m_host, const NcfAdamState* s_host, NcfAdamHyper h,
                    void* stream);
 int ncf_sgd_step(const NcfModel* m_host, const NcfGrads* g_host, float lr, void* stream);

@@ -108,7 +108,9 @@ struct RowsParams {
 
 // mode 0: Adam step on the touched rows; mode 1: flush (all rows, replay only);
 // mode 2: catch-up (touched rows, replay only) — run BEFORE the forward of a step so that the rows
-// the batch is about to read are at the dense-Adam state of the previous step.
+// the batch is about to read are at the dense-Adam state of the previous step;
+// mode 3: Adam step on ALL rows (the reference's dense optimiser as it is): when a step touches a
+// large share of the tables, streaming every row once is cheaper than list + catch-up + row gather.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q) {
   __shared__ float c1_sm[kWarps][kMaxReplay];
@@ -117,11 +119,13 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
   float* c1s = c1_sm[warp];
   float* c2s = c2_sm[warp];
   const int64_t step_now = *q.step;
-  const int64_t t = (MODE == 0) ? step_now + 1 : step_now;  // state is brought to "after step t"
+  constexpr bool kStep = (MODE == 0 || MODE == 3);   // consumes gradients
+  constexpr bool kList = (MODE == 0 || MODE == 2);   // iterates the touched lists
+  const int64_t t = kStep ? step_now + 1 : step_now;  // state is brought to "after step t"
   const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
   const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
   int64_t n0, n1;
-  if (MODE != 1) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
+  if (kList) { n0 = q.tcount[0]; n1 = q.tcount[1]; } else { n0 = q.rows[0]; n1 = q.rows[1]; }
   const int64_t total = n0 + n1;
   const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
   // Fast path (NeuMF with rows of at most 128 floats, the bench shapes): a lane owns one float4 of the
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
       r = 0;
       last = 0;
       if (e < total) {
-        r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+        r = kList ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
         last = q.last[side][r];
       }
     };
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
     for (int64_t e = wid; e < total; e += nw, side = nside, r = nr, last = nlast) {
       fetch(e + nw, nside, nr, nlast);
       int gap;
-      if (MODE == 0) {
+      if (kStep) {
         gap = (last > 0) ? (int)(t - 1 - last) : 0;
       } else {
         if (last <= 0 || last >= t) continue;
@@ -157,13 +161,13 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
         pg = *reinterpret_cast<const float4*>(q.p_gmf[side] + og);
         mg = *reinterpret_cast<const float4*>(q.m_gmf[side] + og);
         vg = *reinterpret_cast<const float4*>(q.v_gmf[side] + og);
-        if (MODE == 0) gg = *reinterpret_cast<const float4*>(q.g_gmf[side] + og);
+        if (kStep) gg = *reinterpret_cast<const float4*>(q.g_gmf[side] + og);
       }
       if (lm) {
         pm = *reinterpret_cast<const float4*>(q.p_mlp[side] + om);
         mm = *reinterpret_cast<const float4*>(q.m_mlp[side] + om);
         vm = *reinterpret_cast<const float4*>(q.v_mlp[side] + om);
-        if (MODE == 0) gm = *reinterpret_cast<const float4*>(q.g_mlp[side] + om);
+        if (kStep) gm = *reinterpret_cast<const float4*>(q.g_mlp[side] + om);
       }
       __syncwarp();
       const int n = min(gap, kMaxReplay);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
       for (int k = 0; k < 4; ++k) {
         replay_zero_steps(a[0][k], a[1][k], a[2][k], gap, c1s, c2s, q.c);
         replay_zero_steps(a[4][k], a[5][k], a[6][k], gap, c1s, c2s, q.c);
-        if (MODE == 0) {
+        if (kStep) {
           adam_real_step(a[0][k], a[1][k], a[2][k], a[3][k], c1t, c2t, q.c);
           adam_real_step(a[4][k], a[5][k], a[6][k], a[7][k], c1t, c2t, q.c);
         }
@@ -187,27 +191,27 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
         *reinterpret_cast<float4*>(q.p_gmf[side] + og) = pg;
         *reinterpret_cast<float4*>(q.m_gmf[side] + og) = mg;
         *reinterpret_cast<float4*>(q.v_gmf[side] + og) = vg;
-        if (MODE == 0) *reinterpret_cast<float4*>(q.g_gmf[side] + og) = make_float4(0, 0, 0, 0);
+        if (kStep) *reinterpret_cast<float4*>(q.g_gmf[side] + og) = make_float4(0, 0, 0, 0);
       }
       if (lm) {
         *reinterpret_cast<float4*>(q.p_mlp[side] + om) = pm;
         *reinterpret_cast<float4*>(q.m_mlp[side] + om) = mm;
         *reinterpret_cast<float4*>(q.v_mlp[side] + om) = vm;
-        if (MODE == 0) *reinterpret_cast<float4*>(q.g_mlp[side] + om) = make_float4(0, 0, 0, 0);
+        if (kStep) *reinterpret_cast<float4*>(q.g_mlp[side] + om) = make_float4(0, 0, 0, 0);
       }
       if (lane == 0) {
         q.last[side][r] = (int32_t)t;
-        if (MODE == 0) q.flag[side][r] = 0;
+        if (kStep) q.flag[side][r] = 0;
       }
     }
     return;
   }
   for (int64_t e = wid; e < total; e += nw) {
     const int side = e < n0 ? 0 : 1;
-    const int64_t r = (MODE != 1) ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+    const int64_t r = kList ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
     const int32_t last = q.last[side][r];
     int gap;
-    if (MODE == 0) {
+    if (kStep) {
       gap = (last > 0) ? (int)(t - 1 - last) : 0;
     } else {
       if (last <= 0 || last >= t) continue;
@@ -223,19 +227,19 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
     __syncwarp();
     if (q.has_gmf) {
       const int64_t o = r * q.f;
-      float* G = (MODE == 0) ? q.g_gmf[side] + o : nullptr;
+      float* G = kStep ? q.g_gmf[side] + o : nullptr;
       if (vec) adam_row<4>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
       else adam_row<1>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, G, q.f, gap, c1s, c2s, c1t, c2t, q.c, lane);
     }
     if (q.has_mlp) {
       const int64_t o = r * q.d;
-      float* G = (MODE == 0) ? q.g_mlp[side] + o : nullptr;
+      float* G = kStep ? q.g_mlp[side] + o : nullptr;
       if (vec) adam_row<4>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
       else adam_row<1>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, G, q.d, gap, c1s, c2s, c1t, c2t, q.c, lane);
     }
     if (lane == 0) {
       q.last[side][r] = (int32_t)t;
-      if (MODE == 0) q.flag[side][r] = 0;
+      if (kStep) q.flag[side][r] = 0;
     }
   }
 }
@@ -324,6 +328,73 @@ __global__ void mark_side_kernel(const int64_t* __restrict__ rows, int64_t n, in
   }
 }
 
+// ---- the all-rows step as a streaming kernel ------------------------------------------------------------
+// blockIdx.y = table (user GMF, item GMF, user MLP, item MLP); a thread owns float4s of the table taken as
+// one flat array, so the four streams p, m, v, g are read and written fully coalesced.  `last` is only
+// read here (both tables of a row need the same gap); stamp_rows_kernel sets it afterwards.
+struct FlatTable {
+  float *p, *m, *v, *g;
+  const int32_t* last;
+  int64_t n4;   // float4s in the table
+  int q4;       // float4s per row
+};
+struct FlatParams {
+  FlatTable tab[4];
+  const int64_t* step;
+  AdamConst c;
+};
+
+__device__ __forceinline__ void replay_inline(float& p, float& m, float& v, int last, int gap, const AdamConst& c) {
+  const int n = min(gap, kMaxReplay);
+  const float m0 = m, v0 = v;
+  float mm = m0, r = sqrtf(v0);
+  if (m0 != 0.f) {
+    for (int j = 0; j < n; ++j) {
+      const float s = (float)(last + 1 + j);
+      mm *= c.b1;
+      r *= c.sqrt_b2;
+      p -= bias_c1(c, s) * __fdividef(mm, fmaf(r, bias_c2(c, s), c.eps));
+    }
+  }
+  m = m0 * expf((float)gap * c.ln_b1);
+  v = v0 * expf((float)gap * c.ln_b2);
+}
+
+__global__ void __launch_bounds__(256) adam_flat_kernel(const FlatParams q) {
+  const FlatTable T = q.tab[blockIdx.y];
+  if (T.n4 == 0) return;
+  const int64_t t = *q.step + 1;
+  const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
+  float4* P = reinterpret_cast<float4*>(T.p);
+  float4* M = reinterpret_cast<float4*>(T.m);
+  float4* V = reinterpret_cast<float4*>(T.v);
+  float4* G = reinterpret_cast<float4*>(T.g);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T.n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p4 = P[i], m4 = M[i], v4 = V[i];
+    const float4 g4 = G[i];
+    const int32_t last = __ldg(&T.last[i / T.q4]);
+    const int gap = (last > 0) ? (int)(t - 1 - last) : 0;
+    float* pp = &p4.x; float* mp = &m4.x; float* vp = &v4.x;
+    const float* gp = &g4.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (gap > 0) replay_inline(pp[k], mp[k], vp[k], last, gap, q.c);
+      adam_real_step(pp[k], mp[k], vp[k], gp[k], c1t, c2t, q.c);
+    }
+    P[i] = p4; M[i] = m4; V[i] = v4;
+    G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void stamp_rows_kernel(int32_t* last_u, int32_t* flag_u, int64_t nu, int32_t* last_i, int32_t* flag_i,
+                                  int64_t ni, const int64_t* step) {
+  const int32_t t = (int32_t)(*step + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nu + ni; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nu) { last_u[i] = t; flag_u[i] = 0; }
+    else { last_i[i - nu] = t; flag_i[i - nu] = 0; }
+  }
+}
+
 __global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
   if (step) *step += 1;
   tcount[0] = 0;
@@ -400,8 +471,21 @@ int check_grads(const NcfModel* m, const NcfGrads* g) {
 
 }  // namespace
 
+static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
+                          void* stream, bool all_rows);
+
 extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
                              NcfAdamHyper h, void* stream) {
+  return adam_step_impl(m, g, s, h, stream, false);
+}
+
+extern "C" int ncf_adam_step_dense(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
+                                   NcfAdamHyper h, void* stream) {
+  return adam_step_impl(m, g, s, h, stream, true);
+}
+
+static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
+                          void* stream, bool all_rows) {
   int rc = ncf::validate_model(m);
   if (rc != NCF_OK) return rc;
   if ((rc = check_grads(m, g)) != NCF_OK) return rc;
@@ -412,8 +496,31 @@ extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdam
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);
-  adam_rows_kernel<0><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
-  NCF_LAUNCH_CHECK("adam_rows_kernel");
+  const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
+  if (all_rows && vec) {
+    FlatParams fp{};
+    fp.step = q.step;
+    fp.c = q.c;
+    for (int side = 0; side < 2; ++side) {
+      if (q.has_gmf)
+        fp.tab[side] = FlatTable{q.p_gmf[side], q.m_gmf[side], q.v_gmf[side], q.g_gmf[side], q.last[side],
+                                 q.rows[side] * q.f / 4, q.f / 4};
+      if (q.has_mlp)
+        fp.tab[2 + side] = FlatTable{q.p_mlp[side], q.m_mlp[side], q.v_mlp[side], q.g_mlp[side], q.last[side],
+                                     q.rows[side] * q.d / 4, q.d / 4};
+    }
+    adam_flat_kernel<<<dim3(ncf::num_sms() * 4, 4), 256, 0, st>>>(fp);
+    NCF_LAUNCH_CHECK("adam_flat_kernel");
+    stamp_rows_kernel<<<ncf::num_sms(), 256, 0, st>>>(q.last[0], q.flag[0], q.rows[0], q.last[1], q.flag[1], q.rows[1],
+                                                     q.step);
+    NCF_LAUNCH_CHECK("stamp_rows_kernel");
+  } else if (all_rows) {
+    adam_rows_kernel<3><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+    NCF_LAUNCH_CHECK("adam_rows_kernel");
+  } else {
+    adam_rows_kernel<0><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+    NCF_LAUNCH_CHECK("adam_rows_kernel");
+  }
   DenseParams dq{};
   fill_dense(dq, m);
   dq.g = g->g_tower; dq.m = s->m_tower; dq.v = s->v_tower; dq.step = s->step; dq.c = q.c;

@@ -86,11 +86,14 @@ class ReplicatedDataParallel:
 
     def step(self, user, item, label):
         ts = self.ts
-        gu, gi = gather_indices(user, item, self.world)
-        if ts.optimizer == "adam":
-            ops.adam_prepare(ts._m, ts._g, ts._s, gu, gi, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
-        else:
+        if ts.optimizer != "adam":
             raise NotImplementedError("replicated DP is implemented for Adam")
+        # a global batch that touches a large share of the tables runs the optimiser over all rows
+        # (the dense Adam of the reference as it is): no index exchange, no catch-up, no row gather
+        dense = ts.dense_adam(user.numel() * self.world)
+        if ts._dirty or not dense:
+            gu, gi = gather_indices(user, item, self.world)
+            ops.adam_prepare(ts._m, ts._g, ts._s, gu, gi, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
         ops.train_step_grads(ts._m, ts._g, user, item, label, None, 1.0, ts.loss_accum, ts.workspace)
         flat = ts.grads.flat
         if self.comm_stream is not None and dist.get_backend() == "nccl":
@@ -101,8 +104,12 @@ class ReplicatedDataParallel:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         else:
             average_(flat, self.world)
-        ops.adam_step(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
-        ts._dirty = True
+        if dense:
+            ops.adam_step_dense(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
+            ts._dirty = False
+        else:
+            ops.adam_step(ts._m, ts._g, ts._s, ts.lr, ts.betas[0], ts.betas[1], ts.eps)
+            ts._dirty = True
         ts.num_steps += 1
 
     def replica_divergence(self) -> float:

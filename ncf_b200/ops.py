@@ -298,6 +298,13 @@ def adam_step(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, beta2=0.
           "ncf_adam_step")
 
 
+def adam_step_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """The Adam step over every row of the tables (no touched lists, no catch-up needed afterwards)."""
+    check(_lib.load().ncf_adam_step_dense(C.byref(m), C.byref(g), C.byref(s),
+                                          NcfAdamHyper(lr, beta1, beta2, eps), current_stream()),
+          "ncf_adam_step_dense")
+
+
 def adam_flush(m: NcfModel, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().ncf_adam_flush(C.byref(m), C.byref(s), NcfAdamHyper(lr, beta1, beta2, eps),
                                      current_stream()), "ncf_adam_flush")

@@ -52,6 +52,9 @@ class FusedTrainStep:
             for p in teacher.parameters():  # reference src/distillation/base.py:16-18
                 p.requires_grad = False
         self._dirty = False  # True while some rows lag behind the dense-Adam state
+        # Adam over every row instead of the touched rows once a step touches this share of the tables
+        # (expected distinct rows of a uniform batch; NCF_ADAM_DENSE=0/1 forces a mode)
+        self.dense_share = 0.42
 
     def _refresh(self):
         """Re-reads the parameter pointers (they change if the module is moved or reloaded)."""
@@ -59,6 +62,18 @@ class FusedTrainStep:
         self._g = self.grads.struct()
         self._s = self.state.struct() if self.state is not None else None
         self._tm = self.teacher.abi_struct() if self.teacher is not None else None
+
+    def dense_adam(self, global_batch: int) -> bool:
+        """Whether a step of `global_batch` samples should run the optimiser over all rows: the
+        reference's dense Adam literally (ncf_adam_step_dense) instead of list + catch-up + row gather."""
+        import math
+        import os
+        forced = os.environ.get("NCF_ADAM_DENSE")
+        if forced in ("0", "1"):
+            return forced == "1"
+        U, I = self.model.user_num, self.model.item_num
+        touched = U * -math.expm1(-global_batch / U) + I * -math.expm1(-global_batch / I)
+        return touched >= self.dense_share * (U + I)
 
     # -- one optimisation step on a device batch ------------------------------------------------
     def step(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor,
@@ -70,15 +85,21 @@ class FusedTrainStep:
         if self.teacher is not None:
             t_logits = self.teacher_logits[:B]
             ops.forward(self._tm, user, item, out=t_logits)
+        dense = self.optimizer == "adam" and self.dense_adam(B)
         if self.optimizer == "adam":
-            # rows this batch reads must first catch up with the dense-Adam trajectory
-            ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
-                             self.betas[1], self.eps)
+            # rows this batch reads must first catch up with the dense-Adam trajectory — unless every
+            # row is current already (the previous steps ran the optimiser over all rows)
+            if self._dirty or not dense:
+                ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
+                                 self.betas[1], self.eps)
         else:
             ops.mark_rows(self._m, self._g, user, item)
         ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
                              self.loss_accum, self.workspace, logits_out)
-        if self.optimizer == "adam":
+        if dense:
+            ops.adam_step_dense(self._m, self._g, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
+            self._dirty = False
+        elif self.optimizer == "adam":
             ops.adam_step(self._m, self._g, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
             self._dirty = True
         else:
@@ -114,6 +135,8 @@ class StepGraph:
         if n < 1:
             raise _lib.NcfError("window smaller than one batch")
         self.ts, self.n_steps, self.batch = ts, n, batch
+        # a window captured while every row was current contains no catch-up for its first step
+        self.assumes_current = ts.optimizer == "adam" and not ts._dirty
         self.graph = torch.cuda.CUDAGraph()
         # Snapshot and restore the optimiser/parameter state around the warm-up and capture
         # launches so that capturing does not advance training.
@@ -128,12 +151,16 @@ class StepGraph:
             self.graph.capture_end()
         torch.cuda.current_stream().wait_stream(stream)
         ts.num_steps -= n  # capture records, it does not execute
+        self.dirty_after = ts._dirty
+        ts._dirty = not self.assumes_current if ts.optimizer == "adam" else False
 
     def replay(self) -> None:
+        if self.assumes_current and self.ts._dirty:
+            self.ts.flush()
         self.graph.replay()
         self.ts.num_steps += self.n_steps
         if self.ts.optimizer == "adam":
-            self.ts._dirty = True
+            self.ts._dirty = self.dirty_after
 
 
 class HostFedTrainer:

@@ -15,6 +15,13 @@ from tests.util import assert_close, assert_close_adam, group, load_golden
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["0", "1"], ids=["sparse-adam", "dense-adam"])
+def adam_mode(request, monkeypatch):
+    """Every test runs with the optimiser over the touched rows (lazy, with catch-up) and over all rows
+    (ncf_adam_step_dense); FusedTrainStep picks one per step from the batch size otherwise."""
+    monkeypatch.setenv("NCF_ADAM_DENSE", request.param)
+
 TRAIN_CASES = ["train_gmf_f8", "train_mlp_f8_l3", "train_neumf_f8_l3", "train_neumf_f32_l2",
                "train_neumf_f6_l2", "train_neumf_f5_l1", "train_neumf_f64_l3", "train_neumf_f8_l3_sgd"]
 
@@ -374,3 +381,34 @@ def test_graph_window_equals_eager_steps():
         assert abs(a - b) <= 1e-5 * abs(a)
     for k in s0:  # atomics reorder fp32 sums run to run, hence a tolerance rather than equality
         assert_close_adam(s1[k], s0[k], k, rtol=1e-4, outlier_frac=5e-3, outlier_rtol=5e-3)
+
+
+def test_optimiser_mode_switches_keep_the_dense_trajectory(monkeypatch):
+    """Steps alternate between the lazy touched-row optimiser and the all-rows one (small and large
+    batches in one run): the trajectory stays the dense-Adam one of the oracle."""
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep
+    monkeypatch.delenv("NCF_ADAM_DENSE", raising=False)   # automatic choice
+    torch.manual_seed(1)
+    rng = np.random.default_rng(1)
+    U, I, f, L = 120, 90, 8, 2
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev())
+    params = {k: v.copy() for k, v in state_np(model).items()}
+    ts = FusedTrainStep(model, optimizer="adam", lr=1e-3, max_batch=256)
+    opt = onp.DenseAdam(lr=1e-3)
+    modes = []
+    for t in range(24):
+        B = 256 if (t // 3) % 2 else 8       # 256 samples touch most rows, 8 almost none
+        modes.append(ts.dense_adam(B))
+        u = rng.integers(0, U, B)
+        i = rng.integers(0, I, B)
+        y = (rng.random(B) < 0.3).astype(np.float32)
+        logits = onp.forward(params, u, i, "NeuMF-end")
+        _, dl = onp.loss_and_dlogit(logits, y)
+        opt.step(params, onp.backward(params, u, i, "NeuMF-end", dl))
+        ts.step(*(torch.from_numpy(a).to(dev()) for a in (u, i, y)))
+    assert any(modes) and not all(modes)
+    ts.flush()
+    got = state_np(model)
+    for k in params:
+        assert_close_adam(got[k], params[k], k, rtol=5e-5, outlier_frac=5e-3, outlier_rtol=5e-3)

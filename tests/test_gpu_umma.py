@@ -14,6 +14,13 @@ from tests.util import assert_close, assert_close_adam
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["0", "1"], ids=["sparse-adam", "dense-adam"])
+def adam_mode(request, monkeypatch):
+    """Every test runs with the optimiser over the touched rows (lazy, with catch-up) and over all rows
+    (ncf_adam_step_dense); FusedTrainStep picks one per step from the batch size otherwise."""
+    monkeypatch.setenv("NCF_ADAM_DENSE", request.param)
+
 UMMA_CASES = ["train_neumf_f32_l2", "train_neumf_f64_l3"]
 
 
