@@ -76,11 +76,10 @@ class ReplicatedDataParallel:
                 dist.broadcast(p.data, src=0)
         # the row gradients (all of the flat buffer but its tower tail) are reduced on a side stream as
         # soon as they are complete, while the weight-gradient kernel is still running
-        # (measured on B200: +7 % at 4 GPUs, -5 % at 2, where the all-reduce is short and its CTAs mostly
-        # take issue slots from the weight-gradient kernel; NCF_DP_OVERLAP=0/1 overrides)
+        # (opt-in, NCF_DP_OVERLAP=1: measured on B200 it gains 7 % at 4 GPUs but loses 2-6 % at 2 and 8,
+        # where the all-reduce's CTAs mostly take issue slots from the weight-gradient kernel)
         import os
-        want = os.environ.get("NCF_DP_OVERLAP")
-        overlap = (self.world >= 4) if want is None else (want == "1")
+        overlap = os.environ.get("NCF_DP_OVERLAP") == "1"
         self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and overlap) else None
         self.n_rows_flat = (ts.grads.g_tower.data_ptr() - ts.grads.flat.data_ptr()) // 4
 
