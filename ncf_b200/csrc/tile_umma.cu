@@ -1,25 +1,31 @@
 // tcgen05 / TMEM version of the tower arithmetic for large batches (sm_100a).
 //
 // The tower (reference: src/ncf/models.py:86-107, MLP_layers + predict_layer, and autograd's
-// backward of it) is run layer by layer as 128-sample x N_out GEMMs on the 5th-generation tensor
-// cores: `tcgen05.mma.cta_group::1.kind::tf32`, operands read from shared memory through matrix
-// descriptors, fp32 accumulators in tensor memory, one elected thread issuing.  fp32 parity comes
-// from the same error-compensated split the mma.sync kernel uses (x = hi + lo, hi = x with the low
-// 13 mantissa bits cleared): D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+// backward of it) runs as 128-sample x N GEMMs on the 5th-generation tensor cores:
+// `tcgen05.mma.cta_group::1.kind::tf32`, fp32 accumulators in tensor memory.  fp32 parity comes from
+// the error-compensated split the mma.sync kernel uses as well (x = hi + lo, hi = x with the low 13
+// mantissa bits cleared - which is what the tensor core does to an fp32 operand by itself):
+// D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 //
 //   umma_weight_images_kernel   W_k -> swizzled (hi, lo) operand images, forward and transposed
-//   umma_gemm_kernel<EPI>       D[128 x N] = A[128 x K] * Bimg[N x K]^T, warp-specialised:
-//                               4 producer warps (global/gather -> registers -> swizzled smem, split),
-//                               1 MMA warp, 4 epilogue warps (TMEM -> registers -> fused epilogue)
+//   umma_tower_kernel<TRAIN>    fused: gather -> tower forward -> predict / loss -> backward-data ->
+//                               scatter for one 128-sample tile at a time, every A operand in TMEM
+//                               (towers whose operand chain fits the 512 TMEM columns: f <= 64 and
+//                               W[1] <= 128, e.g. the bench config f = 32, L = 3)
+//   umma_gemm_kernel<EPI>       the same GEMMs as separate launches, operands from shared memory
+//                               (fallback for wider towers, e.g. f = 64 with L = 3):
 //       EPI_RELU_STORE  forward layer:  act[k+1] = relu(D + b)
-//       EPI_PREDICT     last layer:     h_L = relu(D + b); logit, loss, dlogit, predict grads,
-//                                       GMF-branch scatter, delta_L
+//       EPI_PREDICT(_TRAIN)  last layer: h_L = relu(D + b); logit (+ loss, dlogit, predict grads,
+//                                       GMF-branch scatter, delta_L)
 //       EPI_MASK_STORE  backward data:  delta[k] = D * (act[k] > 0)
 //       EPI_SCATTER     backward data of layer 0: D -> RED.128 into the embedding-gradient rows
 //   umma_wgrad_kernel           dW_k = delta[k+1]^T act[k] summed over the CTA's samples with the
 //                               accumulator resident in TMEM; both operands MN-major (128B_BASE32B)
 //
-// Layouts verified on hardware by tools/umma_probe.cu (profiles/umma_probe_r01.txt).
+// Layouts, issue rates and hand-off costs were measured on this hardware first: tools/umma_probe.cu,
+// tools/mma_issue_probe.cu, tools/sync_probe.cu (outputs and the kernel's phase trace in profiles/).
+// Debug aids compiled out by default: -DNCF_UMMA_TRACE (clock64 timeline of CTA 0), NCF_UMMA_ABLATE
+// (knock-outs of single ingredients, results are wrong, only the time matters).
 #include <algorithm>
 #include <cstdlib>
 
@@ -33,7 +39,6 @@ constexpr uint32_t kHiMask = 0xffffe000u;
 constexpr int kProducerWarps = 8;   // two groups of four (even / odd panels)
 constexpr int kLoaderWarp = 17;     // weight-panel bulk copies
 constexpr int kGemmThreads = 576;   // warps 0-7 A producers, 8 MMA, 9-12 / 13-16 epilogue (even / odd tiles), 17 loader
-constexpr int kChunk = 32;          // samples per wgrad stage (4 k-steps of 8)
 constexpr int kMaxStages = 4;
 
 enum { EPI_RELU_STORE = 0, EPI_PREDICT = 1, EPI_PREDICT_TRAIN = 2, EPI_MASK_STORE = 3, EPI_SCATTER = 4 };
