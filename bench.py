@@ -67,7 +67,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML (a thread, every 50 ms) during the timed
+    """SM clock and throttle reasons sampled through NVML (a thread, every 5 ms) during the timed
     region — the same fields as the nvidia-smi clocks line of B200_PROFILING.md."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
@@ -100,7 +100,7 @@ class ClockSampler:
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     pass
-                self._stop.wait(0.05)
+                self._stop.wait(0.005)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
@@ -290,8 +290,8 @@ def run_ours(args):
     launches_per_step = 17 if sharded is not None else 7
     if B >= 8192 and f >= 32:   # tcgen05 path: weight images + tower + wgrad instead of split + fused tile
         launches_per_step += 1
-    if sharded is None and ts.dense_adam(B * world):   # no mark / catch-up launches in the all-rows mode
-        launches_per_step -= 2
+    if sharded is None and ts.dense_adam(B * world):   # all-rows mode: no mark / catch-up, row Adam = flat + stamp
+        launches_per_step -= 1
 
     # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
     phases = None
