@@ -1192,7 +1192,8 @@ constexpr int kWgProducerWarps = 8;
 constexpr int kWgProducers = kWgProducerWarps * 32;
 constexpr int kWgradThreads = kWgProducers + 96;  // + three MMA-issuing warps (one per product of the split)
 
-constexpr int kWgStages = 2;  // measured: 4 stages of half-size chunks are slower (104 vs 79 us): hand-offs dominate
+constexpr int kWgStages = 2;  // measured at the bench workload: 2 x 96 KB 79 us, 3 x 72 KB 86 us, 4 x 48 KB 104 us:
+                              // the hand-off per chunk costs more than the copies it would hide
 struct WgradBars {
   uint64_t full[kWgStages], empty[kWgStages], acc_full;
   uint32_t tmem_base;
@@ -1471,7 +1472,8 @@ int launch_wgrad(const TileParams& p, int passes, cudaStream_t st) {
           return NCF_ERR_ARG;
         }
         const int MB = std::min(128, p.W[k + 1] - mb * 128), NB = std::min(256, p.W[k] - nb * 256);
-        int S = std::min(4096 / MB, 8192 / NB) / 8 * 8;  // <= 4 + 8 sixteen-byte pieces per producer thread
+        // samples per stage: 96 KB of (hi, lo) images, i.e. 4 + 8 sixteen-byte pieces per producer thread
+        int S = std::min(4096 / MB, 8192 / NB) / 8 * 8;
         S = std::max(8, std::min(S, 256));
         g.job[g.njobs] = WgradJob{k, mb, nb, 0, 0, S};
         weight[g.njobs] = 1.0 / S;  // hand-offs per sample; every hand-off costs about the same
@@ -1494,7 +1496,7 @@ int launch_wgrad(const TileParams& p, int passes, cudaStream_t st) {
     const int MB = std::min(128, p.W[k + 1] - g.job[j].mb * 128), NB = std::min(256, p.W[k] - g.job[j].nb * 256);
     smem = std::max(smem, (size_t)kWgStages * 2 * (MB + NB) * g.job[j].S * 4);
   }
-  smem += 1024 + 16 * 1024;  // alignment slack + the M=128 descriptor may read past a narrow A' image
+  smem += 1024;  // alignment slack (an M=128 descriptor over a narrow A' image reads on into the same stage)
   NCF_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_wgrad_kernel<<<cta, kWgradThreads, smem, st>>>(p, g);
   NCF_LAUNCH_CHECK("umma_wgrad_kernel");
