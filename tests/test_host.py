@@ -216,3 +216,26 @@ def test_row_shard_layout_helpers():
     for r in range(3):
         rebuilt[r::3] = parts[r]["embed_user_GMF.weight"]
     assert torch.equal(rebuilt, full["embed_user_GMF.weight"])
+
+
+def test_optimiser_mode_heuristic():
+    """FusedTrainStep.dense_adam: all-rows Adam only when a step is expected to touch a large share of
+    the tables (the decision is host logic; it must not need a GPU)."""
+    from ncf_b200.trainer import FusedTrainStep
+
+    class _M:
+        user_num, item_num = 138_493, 26_744
+
+    ts = FusedTrainStep.__new__(FusedTrainStep)
+    ts.model, ts.dense_share = _M(), 0.42
+    assert ts.dense_adam(65_536)            # the bench batch: ~46 % of the rows distinct
+    assert ts.dense_adam(8 * 65_536)        # an 8-GPU global batch touches nearly everything
+    assert not ts.dense_adam(256)           # the reference batch size
+    _M.user_num, _M.item_num = 10_000_000, 1_000_000
+    assert not ts.dense_adam(65_536)        # 10M x 1M tables: < 1 % of the rows per step
+    import os
+    os.environ["NCF_ADAM_DENSE"] = "1"
+    try:
+        assert ts.dense_adam(1)
+    finally:
+        del os.environ["NCF_ADAM_DENSE"]
