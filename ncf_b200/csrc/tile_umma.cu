@@ -641,10 +641,11 @@ umma_gemm_kernel(const __grid_constant__ TileParams p, const __grid_constant__ G
 //     Lo[k] holds X_k (lo), later accumulates dX_k and then holds dZ_k (hi) while dZ_k (lo) replaces
 //     X_k in H[k].  Layer 0's gathered panels go through a ring of 64-column stages laid over
 //     everything but H[1]; dX_0 accumulates in [2 W[1], 2 W[1] + W[0]).
-// Roles: warps 0-7 gather producers (two groups, alternate panels), 8-10 MMA issuers (one thread can
+// Roles: warps 0-7 gather producers (two groups, alternate panels), then the MMA issuers (one thread can
 // start a tcgen05.mma only every ~105 cycles and a tf32 MMA covers just K = 8, so the three products
 // of the split, hi*hi / lo*hi / hi*lo, are issued by three warps into the same accumulator, which the
-// preceding epilogue has zeroed), 11-18 epilogue (lane quarter x column half), 19 weight-panel loader.  Activations and deltas are also written to
+// preceding epilogue has zeroed; two such sets take alternate panels), eight epilogue warps (lane
+// quarter x column half) and the weight-panel loader warp.  Activations and deltas are also written to
 // the HBM scratch for the weight-gradient kernel.
 constexpr int kMaxGemms = 2 * NCF_MAX_LAYERS;
 constexpr int kRingMax = 6;
@@ -728,11 +729,13 @@ __device__ __forceinline__ void store_rows(float (&v)[32], float* dst, int64_t l
     if (r0 + i < nrows) *reinterpret_cast<float4*>(p0 + i * ld) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-constexpr int kTowerThreads = 640;
+constexpr int kTowerMmaSets = 1;     // sets of three issuing warps taking alternate panels (2 sets: the 80-register cap of
+                                     // 736 threads costs the epilogues more than the issue overlap gains: 215 vs 191 us)
+constexpr int kTowerThreads = (8 + 3 * kTowerMmaSets + 8 + 1) * 32;
 constexpr int kTowerEpiWarps = 8;
-constexpr int kTowerMmaWarp = 8;     // .. +2
-constexpr int kTowerEpiWarp0 = 11;
-constexpr int kTowerLoaderWarp = 19;
+constexpr int kTowerMmaWarp = 8;     // .. + 3 * kTowerMmaSets - 1
+constexpr int kTowerEpiWarp0 = kTowerMmaWarp + 3 * kTowerMmaSets;
+constexpr int kTowerLoaderWarp = kTowerEpiWarp0 + kTowerEpiWarps;
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(kTowerThreads, 1)
@@ -753,8 +756,8 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     const int nm = (g.passes == 3) ? 3 : 1;  // MMA-issuing warps, each commits for its own instructions
     for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], 4); mbar_init(&bars.a_empty[s], nm); }
     for (int s = 0; s < kBStages; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], nm); }
-    mbar_init(&bars.acc_ready[0], nm);
-    mbar_init(&bars.acc_ready[1], nm);
+    mbar_init(&bars.acc_ready[0], nm * kTowerMmaSets);
+    mbar_init(&bars.acc_ready[1], nm * kTowerMmaSets);
     mbar_init(&bars.opnd_ready, kTowerEpiWarps);
     mbar_init(&bars.tile_done, kTowerEpiWarps);
     mbar_init(&bars.dl_ready, kTowerEpiWarps / 2);
@@ -919,12 +922,14 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           }
         }
     }
-  } else if (warp >= kTowerMmaWarp && warp < kTowerMmaWarp + 3) {
-    // ===== MMA issuers: warp 8 hi*hi, warp 9 lo*hi, warp 10 hi*lo (accumulators are pre-zeroed) =======================
-    const int pass = warp - kTowerMmaWarp;
+  } else if (warp >= kTowerMmaWarp && warp < kTowerEpiWarp0) {
+    // ===== MMA issuers: per set, one warp each for hi*hi, lo*hi, hi*lo (accumulators are pre-zeroed); the
+    // sets take alternate panels, so the ~0.7 k cycles of barrier waits per panel of one set overlap the
+    // issue of the other ===========================================================================================
+    const int pass = (warp - kTowerMmaWarp) % 3, set = (warp - kTowerMmaWarp) / 3;
     if (lane == 0 && (pass == 0 || g.passes == 3)) {
       int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0, n_opnd = 0;
+      uint32_t pha = 0, phb = 0, n_opnd = 0, n_panel = 0;
       for (int64_t tl = 0; tl < my_tiles; ++tl)
         for (int gi = 0; gi < g.ng; ++gi) {
           const TowerGemm& G = g.gemm[gi];
@@ -936,12 +941,17 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
             ++n_opnd;
             tc_fence_after();
           }
-          if (pass == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi));
-          for (int pi = 0; pi < panels; ++pi) {
+          if (pass == 0 && set == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi));
+          for (int pi = 0; pi < panels; ++pi, ++n_panel) {
+            if ((int)(n_panel % kTowerMmaSets) != set) {  // the other set's panel: only keep the ring cursors in step
+              if (G.a_hi < 0 && ++sa == NA) { sa = 0; pha ^= 1; }
+              if (++sb == kBStages) { sb = 0; phb ^= 1; }
+              continue;
+            }
             uint32_t a_hi, a_lo;
             if (G.a_hi < 0) {
               mbar_wait(&bars.a_full[sa], pha);
-              if (pass == 0 && tl == 1) NCF_TRACE(2, 64 + 3 * pi);
+              if (pass == 0 && set == 0 && tl == 1) NCF_TRACE(2, 64 + 3 * pi);
               a_hi = tmem + g.ring_col + sa * 64;
               a_lo = a_hi + 32;
             } else {
@@ -949,7 +959,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               a_lo = tmem + G.a_lo + pi * 32;
             }
             mbar_wait(&bars.b_full[sb], phb);
-            if (pass == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 1);
+            if (pass == 0 && set == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 1);
             tc_fence_after();
             const uint32_t bhi = smem_u32(smem + (size_t)sb * b_stage);
             // the k-step only moves the start-address field of the descriptor (32 B = 2 units of 16 B)
@@ -966,11 +976,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               if (++sa == NA) { sa = 0; pha ^= 1; }
             }
             tc_commit(&bars.b_empty[sb]);
-            if (pass == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 2);
+            if (pass == 0 && set == 0 && tl == 1 && gi == 0) NCF_TRACE(2, 64 + 3 * pi + 2);
             if (++sb == kBStages) { sb = 0; phb ^= 1; }
           }
           tc_commit(&bars.acc_ready[gi & 1]);
-          if (pass == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi) + 1);
+          if (pass == 0 && set == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi) + 1);
         }
     }
   } else {
