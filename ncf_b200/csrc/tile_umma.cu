@@ -670,6 +670,7 @@ struct TowerArgs {
 struct TowerBars {
   uint64_t a_full[kRingMax], a_empty[kRingMax], b_full[kBStages], b_empty[kBStages];
   uint64_t acc_ready[2], opnd_ready, tile_done, dl_ready;
+  uint64_t panel_ready[8];  // 32-column panel c of the operand the running epilogue is producing is in TMEM
   uint32_t tmem_base;
   float pg[2 * 64 + 8];  // predict-layer gradient of this CTA (the fused kernel serves f <= 64)
   float xch[kTile];      // hand-off between the two epilogue warps of a lane quarter: GMF logit, then dlogit
@@ -759,6 +760,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     mbar_init(&bars.acc_ready[0], nm * kTowerMmaSets);
     mbar_init(&bars.acc_ready[1], nm * kTowerMmaSets);
     mbar_init(&bars.opnd_ready, kTowerEpiWarps);
+    for (int c = 0; c < 8; ++c) mbar_init(&bars.panel_ready[c], 4);  // one warp per lane quarter
     mbar_init(&bars.tile_done, kTowerEpiWarps);
     mbar_init(&bars.dl_ready, kTowerEpiWarps / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -929,7 +931,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     const int pass = (warp - kTowerMmaWarp) % 3, set = (warp - kTowerMmaWarp) / 3;
     if (lane == 0 && (pass == 0 || g.passes == 3)) {
       int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0, n_opnd = 0, n_panel = 0;
+      uint32_t pha = 0, phb = 0, n_opnd = 0, n_panel = 0, ppar = 0;
       for (int64_t tl = 0; tl < my_tiles; ++tl)
         for (int gi = 0; gi < g.ng; ++gi) {
           const TowerGemm& G = g.gemm[gi];
@@ -944,6 +946,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           if (pass == 0 && set == 0) NCF_TRACE(1, 2 * ((int)tl * g.ng + gi));
           for (int pi = 0; pi < panels; ++pi, ++n_panel) {
             if ((int)(n_panel % kTowerMmaSets) != set) {  // the other set's panel: only keep the ring cursors in step
+              if (G.a_hi >= 0 && G.new_operand) ppar ^= 1u << pi;
               if (G.a_hi < 0 && ++sa == NA) { sa = 0; pha ^= 1; }
               if (++sb == kBStages) { sb = 0; phb ^= 1; }
               continue;
@@ -955,6 +958,10 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               a_hi = tmem + g.ring_col + sa * 64;
               a_lo = a_hi + 32;
             } else {
+              if (G.new_operand) {  // the epilogue hands its output over panel by panel
+                mbar_wait(&bars.panel_ready[pi], (ppar >> pi) & 1);
+                ppar ^= 1u << pi;
+              }
               a_hi = tmem + G.a_hi + pi * 32;
               a_lo = tmem + G.a_lo + pi * 32;
             }
@@ -1046,6 +1053,18 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         ++n_acc[gi & 1];
         if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi));
         tc_fence_after();
+        // First clear the accumulators of the GEMMs that consume this epilogue's output (every MMA
+        // accumulates) and let them start: they then follow this epilogue panel by panel.
+        if (gi + 1 == g.ng) {
+          zero_cols(g.gemm[0].d_col, g.gemm[0].N);
+          tc_wait_st();
+        } else if (g.gemm[gi + 1].new_operand) {
+          for (int gj = gi + 1; gj < g.ng && (gj == gi + 1 || !g.gemm[gj].new_operand); ++gj)
+            zero_cols(g.gemm[gj].d_col, g.gemm[gj].N);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive_warp(&bars.opnd_ready);
+        }
         const int N = G.N, k = G.k;
         // column range of this warp: half of the accumulator, whole 32-column chunks
         const int nchunk = N >> 5;
@@ -1068,6 +1087,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) lo[j] = lo_of(v[j]);
               tc_st32(lane_addr + g.lcol[kk] + c0, lo);
             }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
             if (TRAIN) store_rows(v, p.act[kk], N, row - lane, p.B, c0, lane);
           }
 
@@ -1132,6 +1154,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                   for (int j = 0; j < 32; ++j) v[j] = lo_of(z[j]);
                   tc_st32(lane_addr + g.lcol[L] + c0, v);
                 }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
                 store_rows(z, p.delta[L], N, row - lane, p.B, c0, lane);
               }
             }
@@ -1152,6 +1177,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) x[j] = lo_of(v[j]);
               tc_st32(lane_addr + g.hcol[k] + c0, x);
             }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
             store_rows(v, p.delta[k], N, row - lane, p.B, c0, lane);
           }
         } else {
@@ -1170,18 +1198,10 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
             }
           }
         }
-        // clear the accumulators of the GEMMs that start once this epilogue is done
-        if (gi + 1 == g.ng) {
-          zero_cols(g.gemm[0].d_col, g.gemm[0].N);
-        } else if (g.gemm[gi + 1].new_operand) {
-          for (int gj = gi + 1; gj < g.ng && (gj == gi + 1 || !g.gemm[gj].new_operand); ++gj)
-            zero_cols(g.gemm[gj].d_col, g.gemm[gj].N);
-        }
         tc_wait_st();
         tc_fence_before();
         if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi) + 1);
         if (gi + 1 == g.ng) mbar_arrive_warp(&bars.tile_done);
-        else if (g.gemm[gi + 1].new_operand) mbar_arrive_warp(&bars.opnd_ready);
       }
     }
   }
