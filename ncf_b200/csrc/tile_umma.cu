@@ -720,9 +720,8 @@ __device__ __forceinline__ void quad8_transpose(float (&v)[32], int lane) {
     }
   }
 }
-// this lane's columns [c0, c0 + 32) of its row -> dst[row][c0 ..], rows of the warp start at wrow0
-__device__ __forceinline__ void store_rows(float (&v)[32], float* dst, int64_t ld, int64_t wrow0, int64_t nrows, int c0, int lane) {
-  quad8_transpose(v, lane);
+// v after quad8_transpose: this lane's float4 of 8 rows -> dst[row][c0 ..], rows of the warp start at wrow0
+__device__ __forceinline__ void store_rows_t(const float (&v)[32], float* dst, int64_t ld, int64_t wrow0, int64_t nrows, int c0, int lane) {
   const int64_t r0 = wrow0 + (lane & ~7);
   float* p0 = dst + r0 * ld + c0 + 4 * (lane & 7);
 #pragma unroll
@@ -1087,10 +1086,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) lo[j] = lo_of(v[j]);
               tc_st32(lane_addr + g.lcol[kk] + c0, lo);
             }
+            if (TRAIN) quad8_transpose(v, lane);  // shuffle work while the TMEM stores drain
             tc_wait_st();
             tc_fence_before();
             mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
-            if (TRAIN) store_rows(v, p.act[kk], N, row - lane, p.B, c0, lane);
+            if (TRAIN) store_rows_t(v, p.act[kk], N, row - lane, p.B, c0, lane);
           }
 
         } else if (G.kind == 0) {
@@ -1154,10 +1154,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                   for (int j = 0; j < 32; ++j) v[j] = lo_of(z[j]);
                   tc_st32(lane_addr + g.lcol[L] + c0, v);
                 }
+                quad8_transpose(z, lane);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
-                store_rows(z, p.delta[L], N, row - lane, p.B, c0, lane);
+                store_rows_t(z, p.delta[L], N, row - lane, p.B, c0, lane);
               }
             }
           } else {
@@ -1177,10 +1178,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) x[j] = lo_of(v[j]);
               tc_st32(lane_addr + g.hcol[k] + c0, x);
             }
+            quad8_transpose(v, lane);
             tc_wait_st();
             tc_fence_before();
             mbar_arrive_warp(&bars.panel_ready[c0 >> 5]);
-            store_rows(v, p.delta[k], N, row - lane, p.B, c0, lane);
+            store_rows_t(v, p.delta[k], N, row - lane, p.B, c0, lane);
           }
         } else {
           // ---- backward data of layer 0: scatter into the embedding-gradient rows -------------------------------
