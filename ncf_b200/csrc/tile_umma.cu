@@ -1304,8 +1304,9 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
     const int64_t* idx_src = from_user ? p.user : p.item;
     const float* tab = from_user ? p.eum + fo : p.eim + (fo - d);
     const int64_t idx_lim = from_user ? p.U : p.I;
-    int64_t idxv[8];
-    auto issue_idx = [&](int64_t ci) {
+    // two chunks ahead (a chunk's copies are often issued right after the previous chunk's)
+    int64_t idx_even[8], idx_odd[8];
+    auto issue_idx = [&](int64_t ci, int64_t (&idxv)[8]) {
       const int64_t row0 = (local + ci * job.nctas) * S;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -1339,8 +1340,9 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
           const float* src;
           bool ok;
           if (k == 0) {
-            ok = idxv[i] >= 0 && idxv[i] < idx_lim && !off;
-            src = ok ? tab + idxv[i] * d : tab;
+            const int64_t ix = (ci & 1) ? idx_odd[i] : idx_even[i];
+            ok = ix >= 0 && ix < idx_lim && !off;
+            src = ok ? tab + ix * d : tab;
           } else {
             const int64_t row = row0 + sb0 + i * sbs;
             ok = row < p.B && !off;
@@ -1350,7 +1352,10 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (k == 0) issue_idx(ci + 1);
+      if (k == 0) {
+        if (ci & 1) issue_idx(ci + 2, idx_odd);
+        else issue_idx(ci + 2, idx_even);
+      }
       return true;
     };
     auto consume = [&](int64_t ci, int newer) {  // newer: chunks copied after this one, still allowed to be in flight
@@ -1389,7 +1394,10 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
       if (t == 0) NCF_TRACE(0, 2 * (int)ci + 1);
       mbar_arrive_warp(&bars.full[s]);
     };
-    if (k == 0) issue_idx(0);
+    if (k == 0) {
+      issue_idx(0, idx_even);
+      issue_idx(1, idx_odd);
+    }
     int64_t issued = 0;
     for (int64_t ci = 0; ci < my_chunks; ++ci) {
       if (issued == ci) issue(issued++, true);  // nothing staged: wait for the stage
