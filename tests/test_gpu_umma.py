@@ -224,3 +224,33 @@ def test_tf32_mode_training_step_is_close(monkeypatch):
         scale = max(np.max(np.abs(ref[2][k])), 1e-30)
         err = np.abs(got[2][k] - ref[2][k]) / scale
         assert np.mean(err > 2e-2) <= 0.01 and np.median(err) <= 2e-3, (k, float(np.mean(err > 2e-2)))
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("shape", [(24, 18, 64, 3, 40), (24, 18, 64, 3, 128), (200, 100, 32, 3, 40), (300, 200, 32, 2, 500)])
+def test_no_read_of_unwritten_scratch(monkeypatch, fused, shape):
+    """The workspace (operand images, activation / delta scratch) is poisoned with NaN patterns before
+    the step: a kernel that reads a scratch element nobody wrote (short last tile, rows beyond the
+    batch, padded panels) would carry the NaN into the loss or the gradients."""
+    from ncf_b200 import ops
+    from ncf_b200.models import NCF
+    monkeypatch.setenv("NCF_UMMA_MIN_B", "1")
+    monkeypatch.setenv("NCF_UMMA_FUSED", fused)
+    U, I, f, L, B = shape
+    torch.manual_seed(0)
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(tp.dev())
+    g = ops.GradBuffers.allocate(model.abi_type(), f, L, U, I, B, tp.dev())
+    m = model.abi_struct()
+    ws = torch.empty(ops.train_workspace_bytes(m, B), dtype=torch.uint8, device=tp.dev())
+    ws.fill_(0xFF)
+    u = torch.randint(0, U, (B,), device=tp.dev())
+    i = torch.randint(0, I, (B,), device=tp.dev())
+    y = (torch.rand(B, device=tp.dev()) < 0.3).float()
+    loss = torch.zeros(1, dtype=torch.float64, device=tp.dev())
+    logits = torch.empty(B, device=tp.dev())
+    ops.mark_rows(m, g.struct(), u, i)
+    ops.train_step_grads(m, g.struct(), u, i, y, None, 1.0, loss, ws, logits)
+    torch.cuda.synchronize()
+    assert np.isfinite(float(loss.item())) and bool(torch.isfinite(logits).all())
+    for name in ("g_user_gmf", "g_item_gmf", "g_user_mlp", "g_item_mlp", "g_tower"):
+        assert bool(torch.isfinite(getattr(g, name)).all()), name
