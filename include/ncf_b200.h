@@ -233,6 +233,15 @@ int ncf_adam_step(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamS
  * ncf_adam_prepare (ncf_mark_rows is not needed for this entry either). */
 int ncf_adam_step_dense(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
                         NcfAdamHyper h, void* stream);
+/* Optimiser sharding for replicated data parallelism (new design): with parameters,
+ * gradients and moments laid out as flat buffers, every rank reduce-scatters the gradients, updates
+ * its own slice with ncf_adam_range (elementwise Adam at step *step + 1; zeroes g; every row must be
+ * current, i.e. the all-rows mode) and all-gathers the parameters; ncf_adam_finish_dense then stamps
+ * every row as current and increments the step counter. */
+int ncf_adam_range(float* p, float* m, float* v, float* g, int64_t n, const int64_t* step, NcfAdamHyper h,
+                   void* stream);
+int ncf_adam_finish_dense(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
+                          void* stream);
 int ncf_adam_flush(const NcfModel* m_host, const NcfAdamState* s_host, NcfAdamHyper h,
                    void* stream);
 int ncf_sgd_step(const NcfModel* m_host, const NcfGrads* g_host, float lr, void* stream);

@@ -395,6 +395,25 @@ __global__ void stamp_rows_kernel(int32_t* last_u, int32_t* flag_u, int64_t nu, 
   }
 }
 
+// Elementwise Adam step over a flat range (data-parallel optimiser sharding: every rank updates its
+// own slice of the flat parameter buffer; requires every row to be current, i.e. all-rows mode).
+__global__ void __launch_bounds__(256) adam_range_kernel(float4* __restrict__ P, float4* __restrict__ M,
+                                                         float4* __restrict__ V, float4* __restrict__ G, int64_t n4,
+                                                         const int64_t* __restrict__ step, AdamConst c) {
+  const int64_t t = *step + 1;
+  const float c1t = bias_c1(c, (float)t), c2t = bias_c2(c, (float)t);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p4 = P[i], m4 = M[i], v4 = V[i];
+    const float4 g4 = G[i];
+    adam_real_step(p4.x, m4.x, v4.x, g4.x, c1t, c2t, c);
+    adam_real_step(p4.y, m4.y, v4.y, g4.y, c1t, c2t, c);
+    adam_real_step(p4.z, m4.z, v4.z, g4.z, c1t, c2t, c);
+    adam_real_step(p4.w, m4.w, v4.w, g4.w, c1t, c2t, c);
+    P[i] = p4; M[i] = m4; V[i] = v4;
+    G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
   if (step) *step += 1;
   tcount[0] = 0;
@@ -629,6 +648,37 @@ extern "C" int ncf_sgd_step(const NcfModel* m, const NcfGrads* g, float lr, void
   sgd_dense_kernel<<<dim3(32, dq.nseg), 256, 0, st>>>(dq, lr);
   NCF_LAUNCH_CHECK("sgd_dense_kernel");
   finalize_step_kernel<<<1, 1, 0, st>>>(nullptr, g->touched_count);
+  NCF_LAUNCH_CHECK("finalize_step_kernel");
+  return NCF_OK;
+}
+
+
+extern "C" int ncf_adam_range(float* p, float* m, float* v, float* g, int64_t n, const int64_t* step,
+                              NcfAdamHyper h, void* stream) {
+  NCF_REQUIRE(p && m && v && g && step, "ncf_adam_range: null pointer");
+  NCF_REQUIRE(n >= 0 && (n & 3) == 0, "ncf_adam_range: n must be a multiple of 4");
+  NCF_REQUIRE((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0,
+              "ncf_adam_range: pointers must be 16-byte aligned");
+  NCF_REQUIRE(h.beta1 > 0.f && h.beta1 < 1.f && h.beta2 > 0.f && h.beta2 < 1.f && h.eps > 0.f,
+              "ncf_adam_range: bad hyper-parameters");
+  if (n == 0) return NCF_OK;
+  adam_range_kernel<<<ncf::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+      reinterpret_cast<float4*>(g), n / 4, step, make_const(h));
+  NCF_LAUNCH_CHECK("adam_range_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_adam_finish_dense(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, void* stream) {
+  int rc = ncf::validate_model(m);
+  if (rc != NCF_OK) return rc;
+  if ((rc = check_grads(m, g)) != NCF_OK) return rc;
+  if ((rc = check_state(m, s)) != NCF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  stamp_rows_kernel<<<ncf::num_sms(), 256, 0, st>>>(s->user_last_step, g->user_flag, m->user_num, s->item_last_step,
+                                                   g->item_flag, m->item_num, s->step);
+  NCF_LAUNCH_CHECK("stamp_rows_kernel");
+  finalize_step_kernel<<<1, 1, 0, st>>>(s->step, g->touched_count);
   NCF_LAUNCH_CHECK("finalize_step_kernel");
   return NCF_OK;
 }

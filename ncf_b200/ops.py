@@ -305,6 +305,18 @@ def adam_step_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, be
           "ncf_adam_step_dense")
 
 
+def adam_range(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, step: torch.Tensor,
+               lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Elementwise Adam step on flat fp32 slices (optimiser sharding in data-parallel training)."""
+    check(_lib.load().ncf_adam_range(ptr(p), ptr(m), ptr(v), ptr(g), p.numel(), ptr(step),
+                                     NcfAdamHyper(lr, beta1, beta2, eps), current_stream()), "ncf_adam_range")
+
+
+def adam_finish_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState):
+    check(_lib.load().ncf_adam_finish_dense(C.byref(m), C.byref(g), C.byref(s), current_stream()),
+          "ncf_adam_finish_dense")
+
+
 def adam_flush(m: NcfModel, s: NcfAdamState, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().ncf_adam_flush(C.byref(m), C.byref(s), NcfAdamHyper(lr, beta1, beta2, eps),
                                      current_stream()), "ncf_adam_flush")

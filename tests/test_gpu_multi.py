@@ -24,6 +24,21 @@ def test_replicated_dp_two_gpus():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_replicated_dp_sharded_optimiser_two_gpus():
+    """Same check with the optimiser sharded over the ranks (reduce-scatter -> Adam on the own slice of
+    the flat parameter buffer -> all-gather), which runs in the all-rows mode."""
+    import os
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29521", str(ROOT / "tests" / "dp_worker.py")]
+    env = dict(os.environ, NCF_DP_SHARD_ADAM="1", NCF_ADAM_DENSE="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["divergence"] == 0.0          # the all-gather leaves identical parameters everywhere
+    assert res["vs_single_process"] < 2e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_row_sharded_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29519", str(ROOT / "tests" / "shard_worker.py")]
