@@ -175,7 +175,8 @@ def config_dict(workload, n_gpus):
                         f"({U} users x {I} items, ~{total} interactions, 4 neg/pos), batch {B} per GPU, Adam lr 1e-3",
             "batch_per_gpu": B, "global_batch": B * n_gpus,
             "parallelism": (f"row-sharded tables x{n_gpus} (all-to-all)" if workload == "big" and n_gpus > 1
-                            else f"dp{n_gpus}"),
+                            else f"dp{n_gpus}" + (" (replicated tables, optimiser sharded: reduce-scatter / "
+                                                  "Adam on 1/N / all-gather)" if n_gpus >= 4 else "")),
             "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
                   "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
 
@@ -292,6 +293,10 @@ def run_ours(args):
         launches_per_step += 1
     if sharded is None and ts.dense_adam(B * world):   # all-rows mode: no mark / catch-up, row Adam = flat + stamp
         launches_per_step -= 1
+    dp_obj = getattr(sync_grads, "__self__", None)
+    if getattr(dp_obj, "sharded", None) is not None and sharded is None:
+        # sharded optimiser (N >= 4): images, tower, wgrad, adam_range, stamp, finalize (+ a torch memset)
+        launches_per_step = 6
 
     # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
     phases = None
