@@ -21,9 +21,9 @@ ReduceOp.AVG.  The dense all-reduce moves the whole buffer (zeros included); a s
 """
 from __future__ import annotations
 
-import torch
 import os
 
+import torch
 import torch.distributed as dist
 
 from . import ops
@@ -80,7 +80,6 @@ class ReplicatedDataParallel:
         # soon as they are complete, while the weight-gradient kernel is still running
         # (opt-in, NCF_DP_OVERLAP=1: measured on B200 it gains 7 % at 4 GPUs but loses 2-6 % at 2 and 8,
         # where the all-reduce's CTAs mostly take issue slots from the weight-gradient kernel)
-        import os
         overlap = os.environ.get("NCF_DP_OVERLAP") == "1"
         self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and overlap) else None
         self.n_rows_flat = (ts.grads.g_tower.data_ptr() - ts.grads.flat.data_ptr()) // 4
