@@ -14,8 +14,13 @@ the full tables and Adam state and processes its own slice of the global batch. 
      results on every rank, so the replicas apply identical updates and stay bit-identical;
   4. sparse-row Adam over the union of touched rows + dense Adam on the tower.
 The gradient of the global-batch mean loss is the rank-average of the local-mean gradients, hence
-ReduceOp.AVG.  The dense all-reduce moves the whole buffer (zeros included); a sparse
-(index, row) exchange is the planned refinement and does not change results.
+ReduceOp.AVG.  The dense all-reduce moves the whole buffer (zeros included).
+When the global batch touches a large share of the rows (FusedTrainStep.dense_adam) steps 1 and 4
+collapse: no index exchange, no catch-up, the optimiser runs over every row (ncf_adam_step_dense).
+From 4 GPUs the optimiser is additionally sharded (`_setup_sharded`): parameters, gradients and
+moments live in flat buffers with one layout; a step is reduce-scatter of the gradients -> elementwise
+Adam on the rank's own 1/N slice (ncf_adam_range) -> all-gather of the parameters.  Same bytes on the
+wire as the all-reduce, 1/N of the optimiser traffic, replicas still bit-identical.
 
 `partition` / `union_rows` are pure functions so that the plan is testable on CPU (gloo).
 """
