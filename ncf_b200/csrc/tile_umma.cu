@@ -1054,9 +1054,14 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         tc_fence_after();
         // First clear the accumulators of the GEMMs that consume this epilogue's output (every MMA
         // accumulates) and let them start: they then follow this epilogue panel by panel.
+        // (a one-layer tower in inference has a single GEMM: its accumulator is the one this epilogue is
+        // about to read, so it is cleared after the read instead)
+        const bool zero_late = (gi + 1 == g.ng) && G.d_col == g.gemm[0].d_col;
         if (gi + 1 == g.ng) {
-          zero_cols(g.gemm[0].d_col, g.gemm[0].N);
-          tc_wait_st();
+          if (!zero_late) {
+            zero_cols(g.gemm[0].d_col, g.gemm[0].N);
+            tc_wait_st();
+          }
         } else if (g.gemm[gi + 1].new_operand) {
           for (int gj = gi + 1; gj < g.ng && (gj == gi + 1 || !g.gemm[gj].new_operand); ++gj)
             zero_cols(g.gemm[gj].d_col, g.gemm[gj].N);
@@ -1200,6 +1205,7 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
             }
           }
         }
+        if (zero_late) zero_cols(g.gemm[0].d_col, g.gemm[0].N);  // both halves are past the named barrier: the read is over
         tc_wait_st();
         tc_fence_before();
         if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi) + 1);
@@ -1716,7 +1722,11 @@ bool umma_eligible(const TileParams& p) {
   if (p.B < min_b) return false;
   if (p.type == NCF_GMF) return false;
   if (p.f < 32 || p.f > 128 || (p.f & (p.f - 1)) != 0) return false;
-  return true;
+  // the weight-gradient kernel's job table holds 12 [128 x 256] blocks: towers with a wider input
+  // layer (f = 64 with L = 4, f = 128 with L = 3, ...) stay on the mma.sync / generic kernels
+  int blocks = 0;
+  for (int k = 0; k < p.L; ++k) blocks += ((p.W[k + 1] + 127) / 128) * ((p.W[k] + 255) / 256);
+  return blocks <= 12;
 }
 
 int64_t umma_image_floats(const TileParams& p) {

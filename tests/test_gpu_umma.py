@@ -4,6 +4,8 @@ The path is selected for large batches only (NCF_UMMA_MIN_B, default 8192); thes
 threshold so that the small reference goldens and oracle-sized batches run through it, and check
 through ncf_last_tile_path() that they really did.  Same bar as tests/test_gpu_parity.py.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -254,3 +256,52 @@ def test_no_read_of_unwritten_scratch(monkeypatch, fused, shape):
     assert np.isfinite(float(loss.item())) and bool(torch.isfinite(logits).all())
     for name in ("g_user_gmf", "g_item_gmf", "g_user_mlp", "g_item_mlp", "g_tower"):
         assert bool(torch.isfinite(getattr(g, name)).all()), name
+
+
+def _inference_case(model_type, f, L, B, U=900, I=700, seed=3):
+    from ncf_b200.models import NCF
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    model = NCF(U, I, f, L, 0.0, model_type).to(tp.dev()).eval()
+    with torch.no_grad():
+        for lin in model.linears():
+            lin.bias.uniform_(-0.1, 0.1)
+    u = rng.integers(0, U, B)
+    i = rng.integers(0, I, B)
+    with torch.no_grad():
+        got = model(torch.from_numpy(u).to(tp.dev()), torch.from_numpy(i).to(tp.dev())).cpu().numpy()
+    assert_close(got, onp.forward(tp.state_np(model), u, i, model_type), "logits")
+
+
+@pytest.mark.parametrize("model_type", ["NeuMF-end", "MLP"])
+def test_single_layer_tower_inference(force_umma, model_type):
+    """num_layers = 1 in inference: the fused kernel runs a single GEMM per tile, so the accumulator it
+    clears for the next tile is the one the predict epilogue reads (cleared after the read).  The batch
+    is large enough that every CTA walks more than one tile."""
+    _inference_case(model_type, 32, 1, 40000)
+
+
+# Tower shapes beyond the ones above (f = 32 with L = 1..3, f = 64 with L = 3).  They run the same
+# kernels with other panel / block counts; the sweep is opt-in (NCF_TEST_SHAPE_SWEEP=1) until it has
+# been run on the hardware once - see DESIGN.md section 8.
+SWEEP = [("NeuMF-end", 64, 1), ("NeuMF-end", 64, 2), ("MLP", 32, 3), ("MLP", 64, 2), ("NeuMF-end", 32, 4),
+         ("NeuMF-end", 128, 1), ("NeuMF-end", 128, 2)]
+
+
+@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
+@pytest.mark.parametrize("model_type,f,L", SWEEP)
+def test_shape_sweep_matches_oracle(force_umma, model_type, f, L):
+    model, g, ref, _ = _oracle_case(model_type, f, L, 1500)
+    _check_grads(model, g, ref)
+    _inference_case(model_type, f, L, 20000)
+
+
+@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
+@pytest.mark.parametrize("f,L", [(128, 3), (64, 4)])
+def test_wide_towers_stay_off_the_tcgen05_path(monkeypatch, f, L):
+    """More than 12 weight-gradient blocks: umma_eligible() says no and the step runs on the other kernels."""
+    from ncf_b200 import _lib
+    monkeypatch.setenv("NCF_UMMA_MIN_B", "1")
+    model, g, ref, _ = _oracle_case("NeuMF-end", f, L, 600, U=300, I=200)
+    assert _lib.load().ncf_last_tile_path() in (1, 2)
+    _check_grads(model, g, ref)
