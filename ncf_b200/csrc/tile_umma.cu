@@ -1026,11 +1026,11 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
       float dl = 0.f, pre_label = 0.f, pre_teacher = 0.f;
       for (int gi = 0; gi < g.ng; ++gi) {
         const TowerGemm& G = g.gemm[gi];
+        float gd = 0.f;
         if (G.kind == 0 && G.k + 1 == L) {
           // while the last layer is still running: half 1 gathers the GMF rows and reduces the GMF part
           // of the logit, half 0 fetches the label
           if (hf == 1) {
-            float gd = 0.f;
             if (has_gmf && ok) {
               const float* ru = p.eug + u * f;
               const float* ri = p.eig + it * f;
@@ -1042,7 +1042,6 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
                 gd = fmaf(w.w, gu.w * gi4.w, gd);
               }
             }
-            bars.xch[q * 32 + lane] = gd;
           } else if (TRAIN && ok && p.dlogit_in == nullptr) {
             pre_label = p.label[row];
             if (p.teacher != nullptr) pre_teacher = p.teacher[row];
@@ -1052,6 +1051,9 @@ umma_tower_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
         ++n_acc[gi & 1];
         if (warp == kTowerEpiWarp0 + 1 && lane == 0) NCF_TRACE(2, 2 * ((int)tl * g.ng + gi));
         tc_fence_after();
+        // published only now: the accumulator of this tile's last layer is ready, so its layer-0 panels
+        // have been supplied, so gather group 0 is done reading the previous tile's dlogit from xch[]
+        if (G.kind == 0 && G.k + 1 == L && hf == 1) bars.xch[q * 32 + lane] = gd;
         // First clear the accumulators of the GEMMs that consume this epilogue's output (every MMA
         // accumulates) and let them start: they then follow this epilogue panel by panel.
         // (a one-layer tower in inference has a single GEMM: its accumulator is the one this epilogue is
