@@ -6,6 +6,7 @@ missing (stubbed with empty modules; only plotting uses it) and `src.utils.confi
 CWD-relative YAML and mkdirs `results/` on import (we chdir to a scratch copy of the YAML).
 
     python oracle/make_golden.py            # rewrites tests/golden/
+    python oracle/make_golden.py --sweep-only   # only the SWEEP_CASES fixtures
 
 Every fixture records the inputs (initial state_dict, index/label batches) and what the reference
 computed from them (logits, losses, autograd gradients, weights after optimiser steps, HR/NDCG).
@@ -247,10 +248,23 @@ def sampler_stats_case(NCFData, name):
     print(name, "collisions", int(sum(hist[u, i] for u, i in pairs)))
 
 
+# Tower shapes the tcgen05 path accepts beyond the ones above (tests: the opt-in shape sweep)
+SWEEP_CASES = [
+    ("train_neumf_f32_l1", "NeuMF-end", 40, 30, 32, 1, 48, 3, "adam", 1e-3, 21),
+    ("train_mlp_f32_l3", "MLP", 30, 24, 32, 3, 40, 3, "adam", 1e-3, 22),
+    ("train_neumf_f64_l1", "NeuMF-end", 24, 18, 64, 1, 40, 3, "adam", 1e-3, 23),
+    ("train_neumf_f64_l2", "NeuMF-end", 24, 18, 64, 2, 40, 3, "adam", 1e-3, 24),
+]
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     NCF, metrics, ResponseDistillation, NCFData = import_reference()
     torch.set_num_threads(1)
+    for case in SWEEP_CASES:
+        train_case(NCF, *case)
+    if "--sweep-only" in sys.argv:  # leave the other fixtures untouched
+        return
     train_case(NCF, "train_gmf_f8", "GMF", 60, 40, 8, 3, 32, 8, "adam", 1e-3, 1)
     train_case(NCF, "train_mlp_f8_l3", "MLP", 60, 40, 8, 3, 32, 8, "adam", 1e-3, 2)
     train_case(NCF, "train_neumf_f8_l3", "NeuMF-end", 60, 40, 8, 3, 32, 8, "adam", 1e-3, 3, short_last=5)

@@ -296,6 +296,18 @@ def test_shape_sweep_matches_oracle(force_umma, model_type, f, L):
     _inference_case(model_type, f, L, 20000)
 
 
+SWEEP_GOLDENS = ["train_neumf_f32_l1", "train_mlp_f32_l3", "train_neumf_f64_l1", "train_neumf_f64_l2"]
+
+
+@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
+@pytest.mark.parametrize("name", SWEEP_GOLDENS)
+def test_shape_sweep_matches_reference_goldens(force_umma, name):
+    """The same shapes against trajectories of the reference itself (oracle/make_golden.py --sweep-only)."""
+    tp.test_forward_matches_reference(name)
+    tp.test_fused_step_gradients_match_reference(name)
+    tp.test_training_steps_match_reference(name)
+
+
 @pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
 @pytest.mark.parametrize("f,L", [(128, 3), (64, 4)])
 def test_wide_towers_stay_off_the_tcgen05_path(monkeypatch, f, L):

@@ -8,7 +8,9 @@ from oracle import philox as oph
 from tests.util import assert_close, assert_close_adam, group, load_golden
 
 TRAIN_CASES = ["train_gmf_f8", "train_mlp_f8_l3", "train_neumf_f8_l3", "train_neumf_f32_l2",
-               "train_neumf_f6_l2", "train_neumf_f5_l1", "train_neumf_f64_l3", "train_neumf_f8_l3_sgd"]
+               "train_neumf_f6_l2", "train_neumf_f5_l1", "train_neumf_f64_l3", "train_neumf_f8_l3_sgd",
+               # shapes of the opt-in GPU sweep (tests/test_gpu_umma.py)
+               "train_neumf_f32_l1", "train_mlp_f32_l3", "train_neumf_f64_l1", "train_neumf_f64_l2"]
 
 
 def _batch(z, meta, t):
@@ -48,8 +50,10 @@ def test_optimizer_steps_match_reference(name):
         else:
             onp.sgd_step(params, g, meta["lr"])
         if t == 0:
+            # Adam: an element whose gradient is at the eps = 1e-8 scale amplifies fp32 summation noise
+            # (train_neumf_f32_l1 has one with g = 1.9e-8 in a row of 7e-6 gradients) - tests/util.py
             for k, ref in group(z, "after1").items():
-                assert_close(params[k], ref, f"after step 1: {k}")
+                (assert_close_adam if opt is not None else assert_close)(params[k], ref, f"after step 1: {k}")
     check = assert_close_adam if opt is not None else assert_close
     for k, ref in group(z, "final").items():
         check(params[k], ref, f"final {k}")
