@@ -175,8 +175,11 @@ def config_dict(workload, n_gpus):
                         f"({U} users x {I} items, ~{total} interactions, 4 neg/pos), batch {B} per GPU, Adam lr 1e-3",
             "batch_per_gpu": B, "global_batch": B * n_gpus,
             "parallelism": (f"row-sharded tables x{n_gpus} (all-to-all)" if workload == "big" and n_gpus > 1
-                            else f"dp{n_gpus}" + (" (replicated tables, optimiser sharded: reduce-scatter / "
-                                                  "Adam on 1/N / all-gather)" if n_gpus >= 4 else "")),
+                            else f"dp{n_gpus}" + (" (replicated tables, optimiser sharded: "
+                                                  + ("exchange inside the Adam kernel over peer memory)"
+                                                     if os.environ.get("NCF_DP_P2P") == "1" else
+                                                     "reduce-scatter / Adam on 1/N / all-gather)")
+                                                  if n_gpus >= 4 else "")),
             "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
                   "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
 

@@ -242,6 +242,24 @@ int ncf_adam_range(float* p, float* m, float* v, float* g, int64_t n, const int6
                    void* stream);
 int ncf_adam_finish_dense(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
                           void* stream);
+/* The same sharded step with the gradient exchange inside the kernel, for ranks on one NVLink node
+ * (experimental, NCF_DP_P2P=1 in ncf_b200.dist): grad_bufs / param_bufs are HOST arrays of `world`
+ * device pointers - entry r is rank r's flat gradient / parameter buffer, entry `rank` the caller's own,
+ * the others mapped with ncf_ipc_open.  The caller owns elements [lo, lo + n): the kernel averages
+ * that slice over every rank's gradients (peer loads), updates m / v (n elements, local) and stores the
+ * new parameters into every rank's buffer (peer stores).  Bracket it with rank barriers: all gradients
+ * complete before, all ranks done after (then zero the local gradient buffer). */
+int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_bufs, float* m, float* v, int64_t lo, int64_t n,
+                 int32_t world, int32_t rank, const int64_t* step, NcfAdamHyper h, void* stream);
+/* Buffers shared between ranks have to be allocations of their own (CUDA IPC exports whole
+ * allocations): ncf_peer_alloc returns zero-filled device memory of the current device, the only
+ * memory this library ever owns; ncf_ipc_export writes its 64-byte handle, which the peers turn into
+ * a pointer valid on their current device with ncf_ipc_open (undo: ncf_ipc_close, ncf_peer_free). */
+int ncf_peer_alloc(int64_t bytes, void** dev_ptr_out);
+int ncf_peer_free(void* dev_ptr);
+int ncf_ipc_export(const void* dev_ptr, void* handle64);
+int ncf_ipc_open(const void* handle64, void** dev_ptr_out);
+int ncf_ipc_close(void* dev_ptr);
 int ncf_adam_flush(const NcfModel* m_host, const NcfAdamState* s_host, NcfAdamHyper h,
                    void* stream);
 int ncf_sgd_step(const NcfModel* m_host, const NcfGrads* g_host, float lr, void* stream);

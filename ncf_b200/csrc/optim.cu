@@ -414,6 +414,43 @@ __global__ void __launch_bounds__(256) adam_range_kernel(float4* __restrict__ P,
   }
 }
 
+// The same step with the gradient exchange inside the kernel (single node, peer memory over NVLink):
+// the rank owns elements [lo4, lo4 + n4) of the flat layout, reads that slice of EVERY rank's gradient
+// buffer (local + world-1 peer loads, all in flight together), averages in rank order, updates its
+// moments and writes the new parameters into EVERY rank's parameter buffer (peer stores).  Replaces
+// reduce-scatter -> adam_range_kernel -> all-gather; the caller brackets it with two rank barriers.
+struct PeerBufs {
+  const float4* g[8];
+  float4* p[8];
+};
+__global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ PeerBufs b, const float4* own_p,
+                                                       float4* __restrict__ M, float4* __restrict__ V,
+                                                       int64_t lo4, int64_t n4, int world, float inv_world,
+                                                       const int64_t* __restrict__ step, AdamConst c) {
+  const int64_t t = *step + 1;
+  const float c1t = bias_c1(c, (float)t), c2t = bias_c2(c, (float)t);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = lo4 + i;
+    float4 gr[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      gr[r] = (r < world) ? b.g[r][e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p4 = own_p[e], m4 = M[i], v4 = V[i];
+    float4 g4 = gr[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { g4.x += gr[r].x; g4.y += gr[r].y; g4.z += gr[r].z; g4.w += gr[r].w; }
+    g4.x *= inv_world; g4.y *= inv_world; g4.z *= inv_world; g4.w *= inv_world;
+    adam_real_step(p4.x, m4.x, v4.x, g4.x, c1t, c2t, c);
+    adam_real_step(p4.y, m4.y, v4.y, g4.y, c1t, c2t, c);
+    adam_real_step(p4.z, m4.z, v4.z, g4.z, c1t, c2t, c);
+    adam_real_step(p4.w, m4.w, v4.w, g4.w, c1t, c2t, c);
+    M[i] = m4; V[i] = v4;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) b.p[r][e] = p4;
+  }
+}
+
 __global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
   if (step) *step += 1;
   tcount[0] = 0;
@@ -666,6 +703,31 @@ extern "C" int ncf_adam_range(float* p, float* m, float* v, float* g, int64_t n,
       reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
       reinterpret_cast<float4*>(g), n / 4, step, make_const(h));
   NCF_LAUNCH_CHECK("adam_range_kernel");
+  return NCF_OK;
+}
+
+extern "C" int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_bufs, float* m, float* v, int64_t lo,
+                            int64_t n, int32_t world, int32_t rank, const int64_t* step, NcfAdamHyper h,
+                            void* stream) {
+  NCF_REQUIRE(grad_bufs && param_bufs && m && v && step, "ncf_adam_p2p: null pointer");
+  NCF_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "ncf_adam_p2p: world must be 1..8 (one node)");
+  NCF_REQUIRE(lo >= 0 && n >= 0 && (lo & 3) == 0 && (n & 3) == 0, "ncf_adam_p2p: lo and n must be multiples of 4");
+  NCF_REQUIRE((((uintptr_t)m | (uintptr_t)v) & 15) == 0, "ncf_adam_p2p: pointers must be 16-byte aligned");
+  NCF_REQUIRE(h.beta1 > 0.f && h.beta1 < 1.f && h.beta2 > 0.f && h.beta2 < 1.f && h.eps > 0.f,
+              "ncf_adam_p2p: bad hyper-parameters");
+  PeerBufs b{};
+  for (int r = 0; r < world; ++r) {
+    NCF_REQUIRE(grad_bufs[r] && param_bufs[r], "ncf_adam_p2p: null peer buffer");
+    NCF_REQUIRE((((uintptr_t)grad_bufs[r] | (uintptr_t)param_bufs[r]) & 15) == 0,
+                "ncf_adam_p2p: peer buffers must be 16-byte aligned");
+    b.g[r] = reinterpret_cast<const float4*>(grad_bufs[r]);
+    b.p[r] = reinterpret_cast<float4*>(param_bufs[r]);
+  }
+  if (n == 0) return NCF_OK;
+  adam_p2p_kernel<<<ncf::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(
+      b, b.p[rank], reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), lo / 4, n / 4, world,
+      1.f / (float)world, step, make_const(h));
+  NCF_LAUNCH_CHECK("adam_p2p_kernel");
   return NCF_OK;
 }
 

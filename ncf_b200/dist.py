@@ -117,8 +117,15 @@ class ReplicatedDataParallel:
                   ("g_item_gmf", model.embed_item_GMF.weight, "m_item_gmf", "v_item_gmf"),
                   ("g_user_mlp", model.embed_user_MLP.weight, "m_user_mlp", "v_user_mlp"),
                   ("g_item_mlp", model.embed_item_MLP.weight, "m_item_mlp", "v_item_mlp")]
-        gflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
-        pflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        # NCF_DP_P2P=1 (experimental, one NVLink node): gradients and parameters live in buffers the other
+        # ranks can map (CUDA IPC), and the exchange happens inside the optimiser kernel - see _sharded_step
+        p2p = os.environ.get("NCF_DP_P2P") == "1" and 2 <= W <= 8
+        if p2p:
+            gbuf, pbuf = ops.PeerBuffer(n_pad, dev), ops.PeerBuffer(n_pad, dev)
+            gflat, pflat = gbuf.tensor, pbuf.tensor
+        else:
+            gflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+            pflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         mflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)   # staging only: sliced below
         vflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         base = old.data_ptr()
@@ -152,6 +159,14 @@ class ReplicatedDataParallel:
         lo = self.rank * per
         self.sharded = {"per": per, "lo": lo, "g": gflat, "p": pflat,
                         "m": mflat[lo:lo + per].clone(), "v": vflat[lo:lo + per].clone()}
+        if p2p:
+            handles = [None] * W
+            dist.all_gather_object(handles, (gbuf.handle(), pbuf.handle()))
+            self.sharded.update(
+                bufs=(gbuf, pbuf), flag=torch.zeros(1, dtype=torch.float32, device=dev),
+                gptrs=[gbuf.address if r == self.rank else gbuf.open_peer(handles[r][0]) for r in range(W)],
+                pptrs=[pbuf.address if r == self.rank else pbuf.open_peer(handles[r][1]) for r in range(W)])
+            dist.barrier()  # nobody starts stepping before every rank has mapped every buffer
         ts._refresh()
 
     def _sharded_step(self, user, item, label):
@@ -160,6 +175,19 @@ class ReplicatedDataParallel:
             ts.flush()
         ops.train_step_grads(ts._m, ts._g, user, item, label, None, 1.0, ts.loss_accum, ts.workspace)
         lo, per = sh["lo"], sh["per"]
+        if "gptrs" in sh:
+            # One kernel instead of reduce-scatter -> Adam -> all-gather: it reads the own slice of every
+            # rank's gradients and writes the new parameters into every rank's buffer over NVLink.  The two
+            # one-element all-reduces are the rank barriers around it (stream-ordered on every rank).
+            dist.all_reduce(sh["flag"])      # every rank's gradients are complete
+            ops.adam_p2p(sh["gptrs"], sh["pptrs"], sh["m"], sh["v"], lo, self.rank, ts.state.step, ts.lr,
+                         ts.betas[0], ts.betas[1], ts.eps)
+            dist.all_reduce(sh["flag"])      # every rank has read these gradients and written its parameters
+            sh["g"].zero_()
+            ops.adam_finish_dense(ts._m, ts._g, ts._s)
+            ts._dirty = False
+            ts.num_steps += 1
+            return
         mine_g, mine_p = sh["g"][lo:lo + per], sh["p"][lo:lo + per]
         if dist.get_backend() == "nccl":
             dist.reduce_scatter_tensor(mine_g, sh["g"], op=dist.ReduceOp.AVG)

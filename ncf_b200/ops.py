@@ -312,6 +312,56 @@ def adam_range(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tenso
                                      NcfAdamHyper(lr, beta1, beta2, eps), current_stream()), "ncf_adam_range")
 
 
+def adam_p2p(grad_ptrs, param_ptrs, m: torch.Tensor, v: torch.Tensor, lo: int, rank: int, step: torch.Tensor,
+             lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Sharded Adam step with the gradient exchange inside the kernel (ncf_adam_p2p): `grad_ptrs` /
+    `param_ptrs` are the device addresses of every rank's flat gradient / parameter buffer."""
+    world = len(grad_ptrs)
+    ga = (C.c_void_p * world)(*grad_ptrs)
+    pa = (C.c_void_p * world)(*param_ptrs)
+    check(_lib.load().ncf_adam_p2p(ga, pa, ptr(m), ptr(v), lo, m.numel(), world, rank, ptr(step),
+                                   NcfAdamHyper(lr, beta1, beta2, eps), current_stream()), "ncf_adam_p2p")
+
+
+class PeerBuffer:
+    """Zero-filled fp32 device buffer in an allocation of its own (ncf_peer_alloc), so that it can be
+    exported to the other ranks of the node through CUDA IPC.  `.tensor` aliases the memory."""
+
+    def __init__(self, numel: int, device: torch.device):
+        self.numel, self.device = int(numel), device
+        out = C.c_void_p()
+        with torch.cuda.device(device):
+            check(_lib.load().ncf_peer_alloc(self.numel * 4, C.byref(out)), "ncf_peer_alloc")
+        self.address = out.value
+        self.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": "<f4", "data": (self.address, False),
+                                         "version": 2, "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)   # keeps a reference to self
+        self._peers = []
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(_lib.load().ncf_ipc_export(self.address, buf), "ncf_ipc_export")
+        return buf.raw
+
+    def open_peer(self, handle: bytes) -> int:
+        """Address, valid on this rank's device, of the buffer another rank exported."""
+        out = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.load().ncf_ipc_open(C.create_string_buffer(handle, 64), C.byref(out)), "ncf_ipc_open")
+        self._peers.append(out.value)
+        return out.value
+
+    def close(self):
+        lib = _lib.load()
+        for a in self._peers:
+            lib.ncf_ipc_close(a)
+        self._peers = []
+        if self.address:
+            self.tensor = None
+            lib.ncf_peer_free(self.address)
+            self.address = None
+
+
 def adam_finish_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState):
     check(_lib.load().ncf_adam_finish_dense(C.byref(m), C.byref(g), C.byref(s), current_stream()),
           "ncf_adam_finish_dense")

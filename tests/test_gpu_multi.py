@@ -1,6 +1,7 @@
 """Multi-GPU (needs >= 2 devices; skipped otherwise): replicated data-parallel training keeps the
 replicas bit-identical and matches the single-process run at the global batch."""
 import json
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -27,7 +28,6 @@ def test_replicated_dp_two_gpus():
 def test_replicated_dp_sharded_optimiser_two_gpus():
     """Same check with the optimiser sharded over the ranks (reduce-scatter -> Adam on the own slice of
     the flat parameter buffer -> all-gather), which runs in the all-rows mode."""
-    import os
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29521", str(ROOT / "tests" / "dp_worker.py")]
     env = dict(os.environ, NCF_DP_SHARD_ADAM="1", NCF_ADAM_DENSE="1")
@@ -35,6 +35,21 @@ def test_replicated_dp_sharded_optimiser_two_gpus():
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["divergence"] == 0.0          # the all-gather leaves identical parameters everywhere
+    assert res["vs_single_process"] < 2e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("NCF_TEST_P2P") != "1",
+                    reason="needs 2 GPUs; opt-in (NCF_TEST_P2P=1) until it has run on hardware once")
+def test_replicated_dp_p2p_exchange_two_gpus():
+    """Sharded optimiser with the gradient exchange inside the kernel (ncf_adam_p2p over CUDA-IPC peer
+    buffers, NCF_DP_P2P=1) instead of reduce-scatter / all-gather."""
+    cmd = ["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29523", str(ROOT / "tests" / "dp_worker.py")]
+    env = dict(os.environ, NCF_DP_SHARD_ADAM="1", NCF_ADAM_DENSE="1", NCF_DP_P2P="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["divergence"] == 0.0          # one owner computes every element and writes it to all ranks
     assert res["vs_single_process"] < 2e-4
 
 
