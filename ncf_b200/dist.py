@@ -96,6 +96,8 @@ class ReplicatedDataParallel:
         self.sharded = None
         want_shard = os.environ.get("NCF_DP_SHARD_ADAM")
         auto = self.world >= 4 and ts.optimizer == "adam" and ts.dense_adam(ts.max_batch * self.world)
+        if os.environ.get("NCF_DP_P2P") == "1" and self.world >= 2 and ts.optimizer == "adam":
+            auto = True   # the peer-memory exchange (experimental) exists in the sharded step only
         if dev.type == "cuda" and (want_shard == "1" or (want_shard is None and auto)):
             self._setup_sharded()
 
