@@ -61,6 +61,16 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.ncf_forward(ctypes.byref(m), None, None, 4, None, None, 0, None) == -1
     with pytest.raises(_lib.NcfError):
         _lib.check(rc, "ncf_eval_rank")
+    # peer-memory entries: argument checks come before any CUDA call
+    out = ctypes.c_void_p()
+    assert lib.ncf_peer_alloc(0, ctypes.byref(out)) == -1
+    assert lib.ncf_ipc_export(None, ctypes.create_string_buffer(64)) == -1
+    assert lib.ncf_ipc_open(None, ctypes.byref(out)) == -1
+    ptrs = (ctypes.c_void_p * 9)(*([16] * 9))
+    hyper = _lib.NcfAdamHyper(1e-3, 0.9, 0.999, 1e-8)
+    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 0, 4, 9, 0, 16, hyper, None) == -1
+    assert b"world" in lib.ncf_last_error()
+    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 2, 4, 2, 0, 16, hyper, None) == -1   # lo not a multiple of 4
 
 
 def test_no_cpu_fallback():
