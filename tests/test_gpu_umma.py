@@ -12,7 +12,7 @@ import torch
 
 from oracle import ncf_numpy as onp
 from tests import test_gpu_parity as tp
-from tests.util import assert_close, assert_close_adam
+from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
 
