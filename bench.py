@@ -179,7 +179,8 @@ def config_dict(workload, n_gpus):
                                                   + ("exchange inside the Adam kernel over peer memory)"
                                                      if os.environ.get("NCF_DP_P2P") == "1" else
                                                      "reduce-scatter / Adam on 1/N / all-gather)")
-                                                  if n_gpus >= 4 else "")),
+                                                  if n_gpus >= 4 or (n_gpus >= 2 and os.environ.get("NCF_DP_P2P") == "1")
+                                                  else "")),
             "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
                   "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
 
