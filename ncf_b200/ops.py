@@ -351,14 +351,17 @@ class PeerBuffer:
         self._peers.append(out.value)
         return out.value
 
-    def close(self):
-        lib = _lib.load()
+    def close_peers(self):
         for a in self._peers:
-            lib.ncf_ipc_close(a)
+            _lib.load().ncf_ipc_close(a)
         self._peers = []
+
+    def free(self):
+        """Only after every rank has closed its mapping of this buffer (barrier in between)."""
+        self.close_peers()
         if self.address:
             self.tensor = None
-            lib.ncf_peer_free(self.address)
+            _lib.load().ncf_peer_free(self.address)
             self.address = None
 
 
