@@ -20,7 +20,8 @@ collapse: no index exchange, no catch-up, the optimiser runs over every row (ncf
 From 4 GPUs the optimiser is additionally sharded (`_setup_sharded`): parameters, gradients and
 moments live in flat buffers with one layout; a step is reduce-scatter of the gradients -> elementwise
 Adam on the rank's own 1/N slice (ncf_adam_range) -> all-gather of the parameters.  Same bytes on the
-wire as the all-reduce, 1/N of the optimiser traffic, replicas still bit-identical.
+wire as the all-reduce, 1/N of the optimiser traffic, replicas still bit-identical.  NCF_DP_P2P=1
+(experimental) does that exchange inside the optimiser kernel over CUDA-IPC peer buffers (ncf_adam_p2p).
 
 `partition` / `union_rows` are pure functions so that the plan is testable on CPU (gloo).
 """
