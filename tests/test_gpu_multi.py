@@ -38,8 +38,7 @@ def test_replicated_dp_sharded_optimiser_two_gpus():
     assert res["vs_single_process"] < 2e-4
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("NCF_TEST_P2P") != "1",
-                    reason="needs 2 GPUs; opt-in (NCF_TEST_P2P=1) until it has run on hardware once")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_replicated_dp_p2p_exchange_two_gpus():
     """Sharded optimiser with the gradient exchange inside the kernel (ncf_adam_p2p over CUDA-IPC peer
     buffers, NCF_DP_P2P=1) instead of reduce-scatter / all-gather."""

@@ -281,14 +281,13 @@ def test_single_layer_tower_inference(force_umma, model_type):
     _inference_case(model_type, 32, 1, 40000)
 
 
-# Tower shapes beyond the ones above (f = 32 with L = 1..3, f = 64 with L = 3).  They run the same
-# kernels with other panel / block counts; the sweep is opt-in (NCF_TEST_SHAPE_SWEEP=1) until it has
-# been run on the hardware once - see DESIGN.md section 8.
+# Tower shapes beyond the ones above (f = 32 with L = 1..3, f = 64 with L = 3): every other shape
+# umma_eligible() admits.  They run the same kernels with other panel / block counts (first green on
+# hardware in round 2: profiles/r02/pytest_shape_sweep_2gpu.log).
 SWEEP = [("NeuMF-end", 64, 1), ("NeuMF-end", 64, 2), ("MLP", 32, 3), ("MLP", 64, 2), ("NeuMF-end", 32, 4),
          ("NeuMF-end", 128, 1), ("NeuMF-end", 128, 2)]
 
 
-@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
 @pytest.mark.parametrize("model_type,f,L", SWEEP)
 def test_shape_sweep_matches_oracle(force_umma, model_type, f, L):
     model, g, ref, _ = _oracle_case(model_type, f, L, 1500)
@@ -299,7 +298,6 @@ def test_shape_sweep_matches_oracle(force_umma, model_type, f, L):
 SWEEP_GOLDENS = ["train_neumf_f32_l1", "train_mlp_f32_l3", "train_neumf_f64_l1", "train_neumf_f64_l2"]
 
 
-@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
 @pytest.mark.parametrize("name", SWEEP_GOLDENS)
 def test_shape_sweep_matches_reference_goldens(force_umma, name):
     """The same shapes against trajectories of the reference itself (oracle/make_golden.py --sweep-only)."""
@@ -308,7 +306,6 @@ def test_shape_sweep_matches_reference_goldens(force_umma, name):
     tp.test_training_steps_match_reference(name)
 
 
-@pytest.mark.skipif(os.environ.get("NCF_TEST_SHAPE_SWEEP") != "1", reason="opt-in shape sweep")
 @pytest.mark.parametrize("f,L", [(128, 3), (64, 4)])
 def test_wide_towers_stay_off_the_tcgen05_path(monkeypatch, f, L):
     """More than 12 weight-gradient blocks: umma_eligible() says no and the step runs on the other kernels."""
