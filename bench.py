@@ -7,19 +7,27 @@ Workload at N=1: BASELINE.json configs[3] — NeuMF (factor 32, 3 tower layers: 
 on the synthetic MovieLens-20M shape (138 493 users x 26 744 items, ~20M interactions, 4
 negatives per positive), batch 65 536, Adam lr 1e-3.  It is the config the metric "train
 samples/s @1/2/4/8 B200" is quoted on and it fits one GPU; configs[1] (ML-1M shape, batch 256) is
-launch-latency-bound and is a parity-test case (`--workload ml1m` runs it).
-A "step" is one optimisation step on one batch: [catch-up of lagging rows] -> fused
-gather+forward+loss+backward (tcgen05 path at this batch size: weight images, umma_tower_kernel,
-umma_wgrad_kernel) -> sparse-row Adam.  Under torchrun (N>1) every rank runs the same per-GPU
-batch on its own replica (weak scaling); `--workload big` (BASELINE configs[4], 10M x 1M tables)
-row-shards the tables instead.
+launch-latency-bound and is a parity-test case (`--workload ml1m` runs it, and the
+default line reports it under `small_config`).
 
-The JSON line carries `value` (device-resident inputs), `e2e` (pinned host batches through the
+A "step" is one pass of the hot path over one batch: the batch is laid out by the on-device epoch
+stream (ncf_shuffle_epoch: shuffle + batching of this epoch's positives and sampled negatives), then
+fused gather+forward+loss+backward (tcgen05 path at this batch size: weight images,
+umma_tower_kernel, umma_wgrad_kernel), then Adam (touched rows + catch-up, or all rows when the
+batch touches a large share of the tables).  Under torchrun (N>1) every rank owns a contiguous range
+of the users and runs the same per-GPU batch on the samples of its own users (weak scaling; only the
+item-table and tower gradients are all-reduced); the line then also carries `row_sharded`:
+BASELINE configs[4] (10M x 1M tables, f=64) with the tables row-sharded and item rows exchanged by
+all-to-all.  `--workload big` runs that configuration as the main workload.
+
+The JSON line carries `value` (inputs resident in HBM), `e2e` (pinned HOST batches through the
 public API — ncf_b200.trainer.HostFedTrainer on one GPU — with every step's H2D copies and loss
 read-back inside the timed region), `roofline` of the dominant kernel (timed by CUDA events the
-library records between its launches), `cpu_baseline` (the reference's CPU op sequence,
-oracle/torch_port.py, timed on this box's host cores) and the clocks seen during the timed
-region.  `--impl reference` times only that CPU port.
+library records between its launches) with step-level / evaluation / sampler / NVLink views,
+`cpu_baseline` (the reference's own NCF class from oracle/_ref — or the port in oracle/torch_port.py
+when that directory is absent — on this box's host cores), `gpu_eager_reference` (the same reference
+modules under torch eager on this GPU: the existing sm_100 path to beat) and the clocks sampled
+during the timed region.  `--impl reference` times only the CPU reference.
 """
 from __future__ import annotations
 
@@ -40,6 +48,7 @@ WORKLOADS = {
     "big": ("big", 64, 3, 65536),      # BASELINE configs[4]: row-sharded at N>1
 }
 METRIC, UNIT = "NeuMF train samples/s", "samples/s"
+NVLINK_GBS = 900.0   # per direction per GPU (NVLink 5 / NVSwitch, B200_PROFILING.md)
 
 
 def measured_tensor_peak():
@@ -50,8 +59,8 @@ def measured_tensor_peak():
 
 
 def profile_traffic(kernel):
-    """DRAM bytes per launch of the kernel from the committed ncu capture (profiles/traffic.json),
-    or None when no capture of this kernel is on file."""
+    """DRAM bytes per launch of the kernel from the committed `ncu --set full` capture of this
+    command (profiles/traffic.json, re-measured per round), or None when no capture is on file."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         return json.loads(p.read_text()).get(kernel)
@@ -67,7 +76,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML (a thread, every 5 ms) during the timed
+    """SM clock and throttle reasons sampled through NVML (a thread, every 1 ms) during the timed
     region — the same fields as the nvidia-smi clocks line of B200_PROFILING.md."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
@@ -100,7 +109,7 @@ class ClockSampler:
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     pass
-                self._stop.wait(0.005)
+                self._stop.wait(0.001)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
@@ -117,35 +126,113 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------------------------
+# ---- the reference's own implementation of the path (CPU arm, GPU-eager bar) --------------------------
+class ReferenceTrainer:
+    """The reference inner loop, verbatim in structure (scripts/train_neumf.py:86-90,106-118):
+    `NCF(...)` + `nn.BCEWithLogitsLoss()` + `optim.Adam(model.parameters(), lr)`; per step
+    zero_grad / forward / loss / backward / optimizer.step / loss.item().  The NCF class is the
+    reference's own (oracle/_ref, kind "reference"); when that directory is absent the op-for-op
+    port of oracle/torch_port.py (kind "port") stands in."""
+
+    def __init__(self, U, I, f, L, device, lr=1e-3, seed=0):
+        import torch
+        from oracle import build_ref
+        self.torch, self.device = torch, device
+        ref = build_ref.load()
+        torch.manual_seed(seed)
+        if ref is not None:
+            self.kind = "reference"
+            self.model = ref.NCF(U, I, f, L, 0.0, "NeuMF-end").to(device)
+            self.model.train()
+            self.criterion = torch.nn.BCEWithLogitsLoss()
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)
+            self._port = None
+        else:
+            from oracle import torch_port as tp
+            self.kind = "port"
+            P = tp.init_params(U, I, f, L, "NeuMF-end", seed=seed)
+            if device.type != "cpu":
+                P = {k: v.detach().to(device).requires_grad_(True) for k, v in P.items()}
+            self._port = tp.CpuTrainer(P, "NeuMF-end", lr=lr)
+
+    def step(self, user, item, label):
+        if self._port is not None:
+            return self._port.step(user, item, label)
+        self.model.zero_grad()
+        prediction = self.model(user, item)
+        loss = self.criterion(prediction, label)
+        loss.backward()
+        self.optimizer.step()
+        return loss.item()
+
+
+def reference_batches(U, I, B, n, device, seed=1):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        out.append((torch.randint(0, U, (B,), generator=g).to(device), torch.randint(0, I, (B,), generator=g).to(device),
+                    (torch.rand(B, generator=g) < 0.2).float().to(device)))
+    return out
+
+
 def cpu_reference_run(workload, steps, warmup, budget_s=None):
-    """Times the reference's CPU op sequence (oracle/torch_port.py) on this box's host cores on
-    the same config: one step = one batch of the workload's size through forward, BCE, autograd
-    backward (dense embedding grads) and dense Adam.  Returns (samples/s, ms/step, steps, cores)."""
+    """Times the reference's CPU implementation of the path on this box's host cores on the same
+    config: one step = one batch of the workload's size through forward, BCE, autograd backward (dense
+    embedding grads) and dense Adam.  Returns (samples/s, ms/step, steps, threads, kind)."""
     import torch
     from ncf_b200.synth import SHAPES
-    from oracle import torch_port as tp
     shape, f, L, B = WORKLOADS[workload]
     U, I, _, _ = SHAPES[shape]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    P = tp.init_params(U, I, f, L, "NeuMF-end", seed=0)
-    tr = tp.CpuTrainer(P, "NeuMF-end", lr=1e-3)
-    g = torch.Generator().manual_seed(1)
-    n_distinct = 4
-    batches = [(torch.randint(0, U, (B,), generator=g), torch.randint(0, I, (B,), generator=g),
-                (torch.rand(B, generator=g) < 0.2).float()) for _ in range(n_distinct)]
+    dev = torch.device("cpu")
+    tr = ReferenceTrainer(U, I, f, L, dev)
+    batches = reference_batches(U, I, B, 4, dev)
     for w in range(warmup):
-        tr.step(*batches[w % n_distinct])
+        tr.step(*batches[w % 4])
     t0 = time.perf_counter()
     done = 0
     for k in range(steps):
-        tr.step(*batches[k % n_distinct])
+        tr.step(*batches[k % 4])
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done * B / dt, dt / done * 1e3, done, torch.get_num_threads()
+    return done * B / dt, dt / done * 1e3, done, torch.get_num_threads(), tr.kind
+
+
+def gpu_eager_reference_run(dev, hbm_peak):
+    """The GPU bar to beat: the reference modules under torch eager
+    on this B200 — configs[3] (this bench's workload, 20 steps) and configs[1] (ML-1M shape, f=8 L=3,
+    batch 256, 300 steps).  Timed with CUDA events around the reference loop, `loss.item()` per step
+    included as in the reference."""
+    import torch
+    from ncf_b200.synth import SHAPES
+    out = {}
+    for name, (wl, steps, warm) in {"config4_ml20m_b65536": ("ml20m", 20, 3), "config2_ml1m_b256": ("ml1m", 300, 30)}.items():
+        shape, f, L, B = WORKLOADS[wl]
+        U, I, _, _ = SHAPES[shape]
+        tr = ReferenceTrainer(U, I, f, L, dev)
+        batches = reference_batches(U, I, B, 8, dev)
+        for w in range(warm):
+            tr.step(*batches[w % 8])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            tr.step(*batches[k % 8])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        R = 2 * f + 2 * (f << (L - 1))
+        out[name] = {"samples_per_s": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "kind": tr.kind,
+                     "step_level_hbm_frac": (4 * R * 7 + 24) * B / (ms * 1e-3) / 1e9 / hbm_peak}
+        del tr
+        torch.cuda.empty_cache()
+    out["how"] = ("reference NCF + BCEWithLogitsLoss + dense optim.Adam + loss.item() per step under torch "
+                  f"{torch.__version__} eager on this GPU (fp32, TF32 off = torch default)")
+    return out
 
 
 def run_reference(args):
@@ -153,36 +240,110 @@ def run_reference(args):
     if rank != 0:
         return
     shape, f, L, B = WORKLOADS[args.workload]
-    sps, ms, done, cores = cpu_reference_run(args.workload, args.steps, max(1, args.warmup))
+    sps, ms, done, cores, kind = cpu_reference_run(args.workload, args.steps, max(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.workload, 1),
-        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{done} steps of batch {B} (uniform random indices of the workload's table "
-                                   f"shape), reference op sequence on torch CPU with dense Adam"},
+                                   f"shape): the reference's NCF class, BCEWithLogitsLoss, autograd, dense optim.Adam "
+                                   f"on torch CPU with {cores} threads"},
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def config_dict(workload, n_gpus):
+def config_dict(workload, n_gpus, partitioned=True):
     shape, f, L, B = WORKLOADS[workload]
     from ncf_b200.synth import SHAPES
     U, I, total, _ = SHAPES[shape]
+    if workload == "big" and n_gpus > 1:
+        par = f"row-sharded tables x{n_gpus} (item rows by all-to-all)"
+    elif n_gpus == 1:
+        par = "dp1"
+    elif partitioned:
+        par = (f"dp{n_gpus}: every rank owns 1/{n_gpus} of the users and trains on their samples; item tables + "
+               f"tower replicated, their gradients all-reduced")
+    else:
+        par = f"dp{n_gpus}: fully replicated tables, gradient all-reduce" + (
+            " (exchange inside the Adam kernel over peer memory)" if os.environ.get("NCF_DP_P2P") == "1" else "")
     return {"workload": f"NeuMF f={f} L={L} (tower {f << L}->{f}) on synthetic {shape} shape "
                         f"({U} users x {I} items, ~{total} interactions, 4 neg/pos), batch {B} per GPU, Adam lr 1e-3",
-            "batch_per_gpu": B, "global_batch": B * n_gpus,
-            "parallelism": (f"row-sharded tables x{n_gpus} (all-to-all)" if workload == "big" and n_gpus > 1
-                            else f"dp{n_gpus}" + (" (replicated tables, optimiser sharded: "
-                                                  + ("exchange inside the Adam kernel over peer memory)"
-                                                     if os.environ.get("NCF_DP_P2P") == "1" else
-                                                     "reduce-scatter / Adam on 1/N / all-gather)")
-                                                  if n_gpus >= 4 or (n_gpus >= 2 and os.environ.get("NCF_DP_P2P") == "1")
-                                                  else "")),
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": par,
             "l2": "state touched per step (tables + Adam moments + gradient buffers, ~400 MB at ml20m) "
                   "exceeds the 126 MB L2 and every step uses a different batch; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+def row_sharded_run(dev, world, rank, steps, warmup, tower_math, hbm_peak):
+    """BASELINE configs[4]: NeuMF f=64 L=3 on 10M users x 1M items with the four tables (and their Adam
+    state) row-sharded over the ranks; every rank draws `B` samples of its own users per step and item
+    rows travel by all-to-all (ncf_b200.dist.RowShardedTrainer).  At N=1 the tables live on the one GPU
+    and the step is the plain fused step (the weak-scaling base point)."""
+    import torch
+    import torch.distributed as dist
+    from ncf_b200.dist import RowShardedTrainer, shard_rows
+    from ncf_b200.models import NCF
+    from ncf_b200.synth import SHAPES
+    from ncf_b200.trainer import FusedTrainStep
+    shape, f, L, B = WORKLOADS["big"]
+    U, I = SHAPES["big"][0], SHAPES["big"][1]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Ul, Il = shard_rows(U, world, rank), shard_rows(I, world, rank)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = NCF(Ul, Il, f, L, 0.0, "NeuMF-end")
+    model.tower_math = tower_math
+    need = (warmup + steps) * B
+    bu = torch.randint(0, Ul, (need,), device=dev, generator=g) * world + rank
+    zipf = torch.rand(need, device=dev, generator=g).pow(3.0)                      # popularity skew
+    bi = (zipf * I).long().clamp_(0, I - 1)
+    bl = (torch.rand(need, device=dev, generator=g) < 0.2).float()
+    if world > 1:
+        tr = RowShardedTrainer(model, U, I, lr=1e-3, max_batch=B)
+        step = tr.step
+    else:
+        tr = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+        step = tr.step
+    sl = lambda k: slice(k * B, (k + 1) * B)
+    for k in range(warmup):
+        step(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(warmup, warmup + steps):
+        step(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * steps * B / (ms * 1e-3)
+    d = f << (L - 1)
+    R = 2 * f + 2 * d
+    res = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "n_gpus": world, "scaling": "weak",
+           "config": config_dict("big", world),
+           "resident_gb_per_gpu": torch.cuda.max_memory_allocated(dev) / 1e9,
+           "hbm": {"bytes_per_sample": 4 * R * 7 + 24, "achieved_gbs_per_gpu": (4 * R * 7 + 24) * value / world / 1e9,
+                   "frac": (4 * R * 7 + 24) * value / world / 1e9 / hbm_peak}}
+    if world > 1:
+        stats = tr.wire_stats()
+        out_bytes = stats["bytes_out_per_step"]
+        res["nvlink"] = {"bytes_out_per_gpu_per_step": out_bytes, "peak_gbs_per_direction": NVLINK_GBS,
+                         "achieved_gbs": out_bytes / (ms / steps * 1e-3) / 1e9,
+                         "frac": out_bytes / (ms / steps * 1e-3) / 1e9 / NVLINK_GBS, **stats}
+    del tr, model, bu, bi, bl
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,53 +365,110 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    shape, f, L, B = WORKLOADS[args.workload]
+    hbm_peak, peak_src = measured_peaks()
     K, W = args.steps, max(3, args.warmup)
 
+    if args.workload == "big":
+        res = row_sharded_run(dev, world, rank, K, W, args.tower_math, hbm_peak)
+        if rank == 0:
+            line = {**res, "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "e2e": None, "gpu_launches": (17 if world > 1 else 8) * K, "roofline": None, "cpu_baseline": None}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    st = main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    row_sharded = None
+    if args.workload == "ml20m" and not args.no_row_sharded:
+        row_sharded = row_sharded_run(dev, world, rank, steps=10, warmup=3, tower_math=args.tower_math,
+                                      hbm_peak=hbm_peak)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    B = WORKLOADS[args.workload][3]
+    extras = world == 1 and args.workload == "ml20m" and not args.no_extras
+    # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only) ---------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, done, cores, kind = cpu_reference_run(args.workload, steps=40, warmup=1, budget_s=15.0)
+        cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{done} steps of batch {B} ({ms:.0f} ms/step) of the same config: the reference's "
+                                  f"NCF class + BCEWithLogitsLoss + autograd (dense embedding grads) + dense optim.Adam "
+                                  f"on torch CPU, {cores} threads"}
+    roofline = st["roofline"]
+    sampler = sampler_run(dev, hbm_peak) if extras else None
+    if roofline is not None and sampler is not None:
+        roofline["sampler"] = sampler["roofline"]
+    line = {
+        "metric": METRIC, "value": st["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": st["ms_total"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world, st["dp_partitioned"]),
+        "e2e": {"value": st["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": 8,
+                "ms_per_step": st["e2e_ms"] / K,
+                "launch": "HostFedTrainer: cuda-graph step, next batch H2D overlapped" if world == 1 and not args.no_graph
+                else "eager (NCCL inside the step)",
+                "note": "value's timer is CUDA events on the stream, e2e's is the host clock around the same number of "
+                        "steps; the two agree within run-to-run noise when the copies are hidden"},
+        "gpu_launches": st["launches_per_step"] * K,
+        "clocks": st["clocks"],
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "eval": st["eval_info"],
+        "sampler": sampler,
+        "small_config": small_config_run(dev) if extras else None,
+        "gpu_eager_reference": gpu_eager_reference_run(dev, hbm_peak) if extras else None,
+        "row_sharded": row_sharded,
+        "tower_math": args.tower_math,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
+    """The ml20m / ml1m workload: device-resident timing, per-phase timing, end-to-end timing and
+    evaluation.  Returns plain numbers only, so that every tensor is released when it returns."""
+    import torch
+    import torch.distributed as dist
+
+    from ncf_b200 import ops
+    from ncf_b200.models import NCF
+    from ncf_b200.synth import make_interactions
+    from ncf_b200.trainer import EpochStream, FusedTrainStep
+
+    shape, f, L, B = WORKLOADS[args.workload]
     n_batches = W + K
     need = n_batches * B
-    sharded = None
-    if args.workload == "big":
-        # BASELINE configs[4]: 10M users x 1M items, f=64.  Batches are drawn directly (uniform users,
-        # Zipf-like items); at N>1 the tables are row-sharded and every rank draws its own users.
-        from ncf_b200.synth import SHAPES
-        from ncf_b200.dist import RowShardedTrainer, shard_rows
-        inter = None
-        U, I = SHAPES["big"][0], SHAPES["big"][1]
-        g = torch.Generator(device=dev).manual_seed(1234 + rank)
-        Ul, Il = shard_rows(U, world, rank), shard_rows(I, world, rank)
-        torch.manual_seed(0)
-        with torch.device(dev):
-            model = NCF(Ul, Il, f, L, 0.0, "NeuMF-end")
-        model.tower_math = args.tower_math
-        # samples are partitioned by user (RowShardedTrainer: sharding follows the data); items are global
-        bu = torch.randint(0, Ul, (need,), device=dev, generator=g) * world + rank
-        zipf = torch.rand(need, device=dev, generator=g).pow(3.0)                      # popularity skew
-        bi = (zipf * I).long().clamp_(0, I - 1)
-        bl = (torch.rand(need, device=dev, generator=g) < 0.2).float()
-        if world > 1:
-            sharded = RowShardedTrainer(model, U, I, lr=1e-3, max_batch=B)
-            ts = sharded.ts
-        else:
-            ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
-    else:
-        inter = make_interactions(shape, device=dev)
-        U, I = inter.user_num, inter.item_num
-        torch.manual_seed(0)
-        model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
-        model.tower_math = args.tower_math
-        ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
-        # every rank draws from its own slice of the epoch stream (weak scaling: B per GPU per step)
-        stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=20250605)
-        stream.begin_epoch(0)
-        q0 = rank * need
-        if q0 + need > stream.S:
-            raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
-        bu = torch.empty(need, dtype=torch.int64, device=dev)
-        bi = torch.empty(need, dtype=torch.int64, device=dev)
-        bl = torch.empty(need, dtype=torch.float32, device=dev)
-        stream.fill(q0, need, bu, bi, bl)
-    sl = lambda k: slice(k * B, (k + 1) * B)
+    inter = make_interactions(shape, device=dev)
+    U, I = inter.user_num, inter.item_num
+    torch.manual_seed(0)
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
+    model.tower_math = args.tower_math
+    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    dp = None
+    pos_user, pos_item, p_off = inter.pos_user, inter.pos_item, 0
+    if world > 1:
+        from ncf_b200.dist import ReplicatedDataParallel
+        dp = ReplicatedDataParallel(ts)
+        if dp.partition_users:
+            # the rank's own users: the synthetic positives are sorted by user, so they are one slice
+            p_lo = int(torch.searchsorted(pos_user, torch.tensor(dp.user_lo, device=dev)))
+            p_hi = int(torch.searchsorted(pos_user, torch.tensor(dp.user_hi, device=dev)))
+            pos_user, pos_item, p_off = pos_user[p_lo:p_hi].contiguous(), pos_item[p_lo:p_hi].contiguous(), p_lo
+    # the epoch stream of this rank: negatives for its positives, shuffled, laid out window by window
+    stream = EpochStream(pos_user, pos_item, U, I, num_ng=4, seed=20250605, p_offset=p_off)
+    stream.begin_epoch(0)
+    q0 = 0 if (dp is not None and dp.partition_users) else rank * need
+    if q0 + need > stream.S:
+        raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
+    # two rotating device batches: step k reads buffer k%2 while nothing else touches it
+    bufs = [(torch.empty(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.int64, device=dev),
+             torch.empty(B, dtype=torch.float32, device=dev)) for _ in range(2)]
 
     def barrier():
         if world > 1:
@@ -264,16 +482,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if sharded is not None:
-        sync_grads = sharded.step
-    else:
-        sync_grads = make_dp_sync(ts, world) if world > 1 else None
-
     def one_step(k):
-        if sync_grads is None:
-            ts.step(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+        u, i, y = bufs[k & 1]
+        stream.fill(q0 + k * B, B, u, i, y)          # shuffle + batching of the reference DataLoader, on the device
+        if dp is None:
+            ts.step(u, i, y)
         else:
-            sync_grads(bu[sl(k)], bi[sl(k)], bl[sl(k)])
+            dp.step(u, i, y)
 
     # ---- device-resident timing ------------------------------------------------------------------
     for k in range(W):
@@ -290,58 +505,67 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * K * B / (ms_total * 1e-3)
-    # mark, catch-up, weight split, fused tile, row Adam, tower Adam, finalize; the row-sharded step adds
-    # bucket count/scan/place, a second mark, 2 gathers, 2 permutes and 2 scatter-adds (NCCL kernels not counted)
-    launches_per_step = 17 if sharded is not None else 7
-    if B >= 8192 and f >= 32:   # tcgen05 path: weight images + tower + wgrad instead of split + fused tile
-        launches_per_step += 1
-    if sharded is None and ts.dense_adam(B * world):   # all-rows mode: no mark / catch-up, row Adam = flat + stamp
-        launches_per_step -= 1
-    dp_obj = getattr(sync_grads, "__self__", None)
-    if getattr(dp_obj, "sharded", None) is not None and sharded is None:
-        # sharded optimiser (N >= 4): images, tower, wgrad, adam_range, stamp, finalize (+ a torch memset)
-        launches_per_step = 6
+    dense = ts.dense_adam(B * world)
+    umma = B >= 8192 and f >= 32
+    # shuffle_epoch + [mark, catch-up] + (images, tower, wgrad | split, tile) + (flat, stamp | rows) + tower Adam + finalize
+    launches_per_step = 1 + (0 if dense else 2) + (3 if umma else 2) + (2 if dense else 1) + 2
+    if dp is not None and not dp.partition_users and dp.sharded is not None:
+        launches_per_step = 1 + 3 + 3       # images, tower, wgrad, adam_range (or adam_p2p), stamp, finalize
 
-    # ---- per-phase timing of the same steps (events between the phases) ---------------------------------
-    phases = None
-    if world == 1:
-        names = ["adam_prepare", "train_step_grads", "adam_step"]
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-        # the optimiser mode FusedTrainStep.step picks for this batch size: over all rows (the dense Adam
-        # of the reference as it is, no catch-up phase) or over the touched rows with catch-up
-        dense = ts.dense_adam(B)
+    # materialise the timed batches once more for the per-phase and end-to-end passes
+    bu = torch.empty(need, dtype=torch.int64, device=dev)
+    bi = torch.empty(need, dtype=torch.int64, device=dev)
+    bl = torch.empty(need, dtype=torch.float32, device=dev)
+    stream.fill(q0, need, bu, bi, bl)
+    sl = lambda k: slice(k * B, (k + 1) * B)
 
+    # ---- per-phase timing of the local work of the same steps (events between the phases) ---------------
+    import ctypes as C
+    from ncf_b200 import _lib
+    lib = _lib.load()
+    names = ["shuffle_epoch", "adam_prepare", "train_step_grads", "adam_step"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    u_lo, u_hi = (dp.user_lo, dp.user_hi) if (dp is not None and dp.partition_users) else (0, U)
+    B_norm = B * world if (dp is not None and dp.partition_users) else B
+    if dp is not None and dp.sharded is not None:
+        phases, kernel_ms, tile_path = None, {}, "tcgen05" if umma else "mma.sync"
+    else:
         def phase_prepare(u, i):
             if not dense:
                 ops.adam_prepare(ts._m, ts._g, ts._s, u, i, ts.lr)
 
-        def phase_adam():
-            (ops.adam_step_dense if dense else ops.adam_step)(ts._m, ts._g, ts._s, ts.lr)
+        def phase_grads(u, i, y):
+            ops.train_step_grads_norm(ts._m, ts._g, u, i, y, B_norm, ts.loss_accum, ts.workspace)
 
-        torch.cuda.synchronize()
+        def phase_adam():
+            if dense:
+                ops.adam_step_dense_range(ts._m, ts._g, ts._s, u_lo, u_hi, ts.lr)
+            else:
+                ops.adam_step(ts._m, ts._g, ts._s, ts.lr)
+
+        ts.flush()
+        barrier()
         for k in range(K):
-            u, i, y = bu[sl(W + k)], bi[sl(W + k)], bl[sl(W + k)]
+            u, i, y = bufs[k & 1]
             ev[k][0].record()
-            phase_prepare(u, i)
+            stream.fill(q0 + (W + k) * B, B, u, i, y)
             ev[k][1].record()
-            ops.train_step_grads(ts._m, ts._g, u, i, y, None, 1.0, ts.loss_accum, ts.workspace)
+            phase_prepare(u, i)
             ev[k][2].record()
-            phase_adam()
+            phase_grads(u, i, y)
             ev[k][3].record()
+            phase_adam()
+            ev[k][4].record()
         torch.cuda.synchronize()
-        phases = {n: sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(K)) / K
-                  for j, n in enumerate(names)}
-        # per-kernel times inside ncf_train_step_grads (CUDA events recorded by the library between
-        # its launches; profiling mode synchronises after each step, so outside the timed region)
-        import ctypes as C
-        from ncf_b200 import _lib
-        lib = _lib.load()
+        phases = {n: sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(K)) / K for j, n in enumerate(names)}
+        # per-kernel times inside ncf_train_step_grads (CUDA events recorded by the library between its
+        # launches; profiling mode synchronises after each step, so it is outside the timed region)
         kernel_ms = {}
         lib.ncf_profile_enable(1)
         for k in range(K):
             u, i, y = bu[sl(W + k)], bi[sl(W + k)], bl[sl(W + k)]
             phase_prepare(u, i)
-            ops.train_step_grads(ts._m, ts._g, u, i, y, None, 1.0, ts.loss_accum, ts.workspace)
+            phase_grads(u, i, y)
             phase_adam()
             ms = (C.c_float * 16)()
             nm = C.create_string_buffer(16 * 32)
@@ -351,6 +575,25 @@ def run_ours(args):
                 kernel_ms[key] = kernel_ms.get(key, 0.0) + ms[j] / K
         lib.ncf_profile_enable(0)
         tile_path = {0: "none", 1: "generic", 2: "mma.sync", 3: "tcgen05"}[lib.ncf_last_tile_path()]
+    # the step's collective alone (N>1): the all-reduce of the replicated gradient tail
+    nvlink = None
+    if dp is not None:
+        buf = ts.grads.flat[dp.n_user_flat:] if dp.partition_users else ts.grads.flat
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        c1.record()
+        barrier()
+        buf.zero_()
+        ar_ms = max_over_ranks(c0.elapsed_time(c1) / 10)
+        wire = 2.0 * (world - 1) / world * buf.numel() * 4          # bytes out (= in) per GPU of a ring / NVLS all-reduce
+        nvlink = {"collective": "all_reduce(sum) of " + ("[item GMF | item MLP | tower] gradients"
+                                                           if dp.partition_users else "the whole flat gradient buffer"),
+                  "buffer_bytes": buf.numel() * 4, "ms": ar_ms, "bytes_out_per_gpu": wire,
+                  "achieved_gbs": wire / (ar_ms * 1e-3) / 1e9, "peak_gbs_per_direction": NVLINK_GBS,
+                  "frac": wire / (ar_ms * 1e-3) / 1e9 / NVLINK_GBS, "share_of_step": ar_ms / (ms_total / K)}
 
     # ---- end to end: host buffers, H2D + D2H inside the timed region -----------------------------------
     hu = bu.cpu().pin_memory(); hi = bi.cpu().pin_memory(); hl = bl.cpu().pin_memory()
@@ -364,7 +607,7 @@ def run_ours(args):
     # still copies its own inputs from pinned host memory and reads its loss back.  Multi-GPU steps
     # contain NCCL calls and stay eager.
     hf = None
-    if sync_grads is None and not args.no_graph:
+    if dp is None and not args.no_graph:
         from ncf_b200.trainer import HostFedTrainer
         for k in range(2):  # every kernel loaded before capture
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])
@@ -382,11 +625,11 @@ def run_ours(args):
         du.copy_(hu[sl(k)], non_blocking=True)
         di.copy_(hi[sl(k)], non_blocking=True)
         dl.copy_(hl[sl(k)], non_blocking=True)
-        if sync_grads is None:
+        if dp is None:
             ts.step(du, di, dl)
         else:
-            sync_grads(du, di, dl)
-        host_loss.copy_(sharded.loss_accum if sharded is not None else ts.loss_accum, non_blocking=True)
+            dp.step(du, di, dl)
+        host_loss.copy_(ts.loss_accum, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the reference reads loss.item() every step
         return float(host_loss[0])
 
@@ -399,25 +642,53 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
+    del hf
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    hbm_peak, peak_src = measured_peaks()
-    tensor_peak = measured_tensor_peak()
+    # ---- evaluation throughput (second half of the metric: eval users/s): every rank scores its own users ----
+    from ncf_b200.metrics import evaluate
+    ts.flush()
+    model.eval()
+    tu, tc = inter.test_users, inter.test_cands
+    if dp is not None and dp.partition_users:
+        keep = (tu >= dp.user_lo) & (tu < dp.user_hi)
+        tu, tc = tu[keep].contiguous(), tc[keep].contiguous()
+    elif dp is not None:
+        lo = rank * (tu.numel() // world)
+        hi_ = tu.numel() if rank == world - 1 else lo + tu.numel() // world
+        tu, tc = tu[lo:hi_].contiguous(), tc[lo:hi_].contiguous()
+    with torch.no_grad():
+        evaluate(model, tu, tc, 10)
+        barrier()
+        times = []
+        for _ in range(5):   # median of 5: an occasional 2x outlier was seen on this pool
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            res = evaluate(model, tu, tc, 10)
+            ee1.record()
+            barrier()
+            times.append(max_over_ranks(ee0.elapsed_time(ee1)))
+    ev_ms = sorted(times)[len(times) // 2]
+    n_users = int(inter.test_users.numel())
     d = f << (L - 1)
+    eval_bytes_user = 4 * (f + d) * 101 + 808          # user row once + 100 candidate rows + indices
+    eval_info = {"users_per_s": n_users / (ev_ms * 1e-3), "ms": ev_ms, "users": n_users, "candidates": 100,
+                 "hr10_rank0": float(res.hit.float().mean().item()),
+                 "roofline": {"bound": "hbm", "bytes_per_user": eval_bytes_user,
+                              "achieved_gbs_per_gpu": eval_bytes_user * n_users / world / (ev_ms * 1e-3) / 1e9,
+                              "peak": hbm_peak, "frac": eval_bytes_user * n_users / world / (ev_ms * 1e-3) / 1e9 / hbm_peak}}
+
+    # ---- roofline of the dominant kernel (rank 0's local work) --------------------------------------------
+    tensor_peak = measured_tensor_peak()
     R = 2 * f + 2 * d
     macs = sum((f << (L - k)) * (f << (L - k - 1)) for k in range(L)) + 2 * f   # tower + predict, per sample
     roofline = None
-    if phases is not None:
+    if rank == 0 and phases is not None:
         dom = max(phases, key=phases.get)
-        nu = len(torch.unique(bu[sl(W)])); ni = len(torch.unique(bi[sl(W)]))
+        nu = len(torch.unique(bufs[0][0])); ni = len(torch.unique(bufs[0][1]))
         # algorithmic bytes per launch
-        adam_rows = (U + I) if dense else (nu + ni)
+        adam_rows = ((u_hi - u_lo) + I) if dense else (nu + ni)
         alg_bytes = {
+            "shuffle_epoch": 20 * B + 24 * B,                  # batch out (2 x int64 + f32) + sources in
             "train_step_grads": (4 * R + 24) * B,              # row gather + indices + label/logit
             "adam_step": 8 * 4 * (f + d) * adam_rows,          # g, p, m, v read + p, m, v, 0 written
             "adam_prepare": 0 if dense else 16 * B + 6 * 4 * (f + d) * (nu + ni),
@@ -425,7 +696,6 @@ def run_ours(args):
         hbm = {n: {"algorithmic_bytes": alg_bytes[n], "ms": phases[n],
                    "achieved_gbs": alg_bytes[n] / max(phases[n], 1e-9) / 1e6,
                    "frac": alg_bytes[n] / max(phases[n], 1e-9) / 1e6 / hbm_peak} for n in phases}
-        traffic = profile_traffic(dom)
         if dom == "train_step_grads" and "tower" in kernel_ms:
             # tcgen05 path: ncf_train_step_grads = weight images + umma_tower_kernel (forward and
             # backward-data of the tower, fused with gather / loss / scatter) + umma_wgrad_kernel.
@@ -441,23 +711,24 @@ def run_ours(args):
                         "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0),
                         "algorithmic_flops_per_launch": flops, "launch_ms": kernel_ms["tower"],
                         "kernel_ms": kernel_ms,
+                        "hbm_of_kernel": {"algorithmic_bytes": (4 * R + 24) * B + 4 * R * B,
+                                          "achieved_gbs": ((4 * R + 24) * B + 4 * R * B) / (kernel_ms["tower"] * 1e-3) / 1e9,
+                                          "note": "row gather + indices + per-sample row-gradient REDs of this kernel"},
                         "wgrad": {"kernel": "umma_wgrad_kernel", "launch_ms": kernel_ms.get("wgrad"),
                                   "achieved_tflops": 2.0 * macs * B / (kernel_ms["wgrad"] * 1e-3) / 1e12,
                                   "traffic": profile_traffic("umma_wgrad_kernel")}}
         elif dom == "train_step_grads" and f >= 32:
-            # the fused fwd+bwd kernel is bound by the tensor pipe in fp32-parity (3xTF32) mode:
-            # algorithmic FLOPs = 6 * MACs per sample (forward 2, dgrad 2, wgrad 2)
             flops = 6.0 * macs * B
             achieved = flops / (phases[dom] * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "ncf_mma_tile_kernel (ncf_train_step_grads)",
                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                        "frac": achieved / tensor_peak, "traffic": traffic,
+                        "frac": achieved / tensor_peak, "traffic": profile_traffic(dom),
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); the kernel runs fp32-parity "
                                        "3xTF32 on mma.sync, i.e. 3 TF32 MMAs per algorithmic MAC",
                         "algorithmic_flops_per_launch": flops, "launch_ms": phases[dom]}
         else:
             roofline = {"bound": "hbm", "kernel": dom, "achieved": hbm[dom]["achieved_gbs"], "peak": hbm_peak,
-                        "unit": "GB/s", "frac": hbm[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": hbm[dom]["frac"], "traffic": profile_traffic(dom), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes[dom], "launch_ms": phases[dom]}
         roofline["phase_ms"] = phases
         roofline["tile_path"] = tile_path
@@ -465,56 +736,43 @@ def run_ours(args):
         roofline["hbm_view"] = hbm
         roofline["hbm_peak_gbs"] = hbm_peak
         roofline["step_level"] = {"bytes_per_sample": 4 * R * 7 + 24,
-                                  "achieved_gbs": (4 * R * 7 + 24) * value / 1e9,
-                                  "frac": (4 * R * 7 + 24) * value / 1e9 / hbm_peak}
+                                  "achieved_gbs_per_gpu": (4 * R * 7 + 24) * value / world / 1e9,
+                                  "frac": (4 * R * 7 + 24) * value / world / 1e9 / hbm_peak}
+        roofline["eval"] = eval_info["roofline"]
+        roofline["nvlink"] = nvlink
 
-    # ---- evaluation throughput (second half of the metric: eval users/s) -----------------------------------
-    eval_info = None
-    if world == 1 and inter is not None:
-        from ncf_b200.metrics import evaluate
-        ts.flush()
-        model.eval()
-        n_users = inter.test_users.numel()
-        with torch.no_grad():
-            evaluate(model, inter.test_users, inter.test_cands, 10)
-            torch.cuda.synchronize()
-            times = []
-            for _ in range(5):   # median of 5: an occasional 2x outlier was seen on this pool
-                ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ee0.record()
-                res = evaluate(model, inter.test_users, inter.test_cands, 10)
-                ee1.record()
-                torch.cuda.synchronize()
-                times.append(ee0.elapsed_time(ee1))
-        ev_ms = sorted(times)[len(times) // 2]
-        eval_info = {"users_per_s": n_users / (ev_ms * 1e-3), "ms": ev_ms, "users": n_users, "candidates": 100,
-                     "hr10": float(res.hit.float().mean().item())}
+    return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks,
+                launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,
+                dp_partitioned=(dp.partition_users if dp is not None else True))
 
-    # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only) ---------------------------
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline and inter is not None:   # dense CPU Adam over 10M rows: not bounded
-        sps, ms, done, cores = cpu_reference_run(args.workload, steps=40, warmup=1, budget_s=15.0)
-        cpu_baseline = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{done} steps of batch {B} ({ms:.0f} ms/step) of the same config: reference op "
-                                  f"sequence on torch CPU, dense autograd embedding grads + dense Adam"}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": 8,
-                "ms_per_step": e2e_ms / K, "launch": "HostFedTrainer: cuda-graph step, next batch H2D overlapped" if hf is not None else "eager"},
-        "gpu_launches": launches_per_step * K,
-        "clocks": clocks,
-        "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
-        "eval": eval_info,
-        "small_config": small_config_run(dev) if (world == 1 and args.workload == "ml20m") else None,
-        "tower_math": args.tower_math,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+def sampler_run(dev, hbm_peak):
+    """ng_sample on the GPU for a full epoch of the ml20m shape: CSR build once + one sampler launch.
+    Algorithmic bytes per positive: 8 + 4*num_ng*(1 + ceil(log2 n_u))."""
+    import math
+    import torch
+    from ncf_b200.synth import make_interactions
+    from ncf_b200.trainer import EpochStream
+    inter = make_interactions("ml20m", device=dev)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    stream = EpochStream(inter.pos_user, inter.pos_item, inter.user_num, inter.item_num, num_ng=4, seed=1)
+    e[1].record()
+    stream.begin_epoch(0)
+    e[2].record()
+    stream.begin_epoch(1)
+    e[3].record()
+    torch.cuda.synchronize()
+    P = stream.P
+    n_u = P / inter.user_num
+    bytes_pos = 8 + 4 * 4 * (1 + math.ceil(math.log2(max(n_u, 2))))
+    ms = e[2].elapsed_time(e[3])
+    return {"positives": int(P), "negatives_per_epoch": int(P * 4), "csr_build_ms": e[0].elapsed_time(e[1]),
+            "ng_sample_ms": ms, "negatives_per_s": P * 4 / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "bytes_per_positive": bytes_pos, "achieved_gbs": bytes_pos * P / (ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "frac": bytes_pos * P / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "note": "binary-search probes are dependent 4-byte loads: latency-bound, not bandwidth-bound"}}
 
 
 def small_config_run(dev, epochs_steps: int = 2048):
@@ -559,13 +817,6 @@ def small_config_run(dev, epochs_steps: int = 2048):
             "ng_sample_ms_per_epoch": sample_ms, "negatives_per_epoch": int(stream.P * 4)}
 
 
-def make_dp_sync(ts, world):
-    """Data-parallel step over replicated tables (see ncf_b200/dist.py)."""
-    from ncf_b200.dist import ReplicatedDataParallel
-    dp = ReplicatedDataParallel(ts)
-    return dp.step
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -574,6 +825,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="ml20m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-row-sharded", action="store_true", help="skip the configs[4] sub-result")
+    ap.add_argument("--no-extras", action="store_true", help="skip small_config / sampler / gpu_eager_reference")
     ap.add_argument("--no-graph", action="store_true", help="end-to-end steps launched eagerly instead of as a CUDA graph")
     ap.add_argument("--tower-math", choices=["fp32", "tf32"], default="fp32",
                     help="fp32 = 3xTF32 parity mode (headline); tf32 = single-pass opt-in mode")

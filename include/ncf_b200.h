@@ -130,21 +130,27 @@ int64_t ncf_tower_param_count(int32_t model_type, int32_t factor_num, int32_t nu
 
 /* ---- a1: observed-pair structure --------------------------------------------------------
  * Replaces the dok_matrix fill loop of reference src/data/datasets.py:20-24 by a CSR with
- * sorted columns: rowptr int64[user_num+1], col int32[P].  Duplicate pairs are kept.
+ * sorted columns: rowptr int64[user_num+1], col int32[P].  Duplicate pairs are kept.  Pairs whose user
+ * is outside [0, user_num) are left out; *bad_flag (device int32, nullable) is set to 1 when there was
+ * such a pair or an item outside int32 (the reference's dok_matrix raises IndexError there).
+ * Rows are sorted in shared memory (bitonic; one warp per row <= 256 items, one CTA per row <= 32 768).
  * workspace: ncf_csr_workspace_bytes(P, user_num). */
 int64_t ncf_csr_workspace_bytes(int64_t P, int64_t user_num);
 int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, int64_t P, int64_t user_num,
-                  int64_t* rowptr, int32_t* col, void* workspace, int64_t workspace_bytes,
-                  void* stream);
+                  int64_t* rowptr, int32_t* col, int32_t* bad_flag, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* ---- a2: negative sampler ---------------------------------------------------------------
  * Replaces NCFData.ng_sample (reference src/data/datasets.py:53-69): for positive p and
  * t < num_ng, out_neg_item[p*num_ng + t] is drawn uniformly from [0, item_num) and redrawn
  * while (pos_user[p], j) is an observed pair.  Draw a of sample s = p_offset+p, t uses word
  * a%4 of Philox4x32-10(counter = {s*num_ng+t (lo), (hi), a/4, epoch}, key = seed), mapped to an
- * item by mulhi32(word, item_num).  p_offset lets shards sample disjoint global sample ids. */
+ * item by mulhi32(word, item_num).  p_offset lets shards sample disjoint global sample ids.
+ * A positive whose user is outside [0, user_num), or whose 65 536 draws were all observed pairs (the
+ * reference loops forever on a user who interacted with every item), gets -1: the training kernels
+ * then report a bad index instead of training on an observed pair. */
 int ncf_sample_neg(const int64_t* rowptr, const int32_t* col, const int64_t* pos_user, int64_t P,
-                   int64_t p_offset, int32_t num_ng, int64_t item_num, uint64_t seed,
+                   int64_t p_offset, int64_t user_num, int32_t num_ng, int64_t item_num, uint64_t seed,
                    uint64_t epoch, int64_t* out_neg_item, void* stream);
 
 /* ---- a3: epoch shuffle + batching ---------------------------------------------------------
@@ -233,6 +239,11 @@ int ncf_adam_step(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamS
  * ncf_adam_prepare (ncf_mark_rows is not needed for this entry either). */
 int ncf_adam_step_dense(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
                         NcfAdamHyper h, void* stream);
+/* The all-rows step restricted to user rows [user_lo, user_hi) (and every item row): data-parallel
+ * ranks that each train on the samples of their own range of users (new design) own
+ * those user rows - the other user rows are never read or written on this rank. */
+int ncf_adam_step_dense_range(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
+                              NcfAdamHyper h, int64_t user_lo, int64_t user_hi, void* stream);
 /* Optimiser sharding for replicated data parallelism (new design): with parameters,
  * gradients and moments laid out as flat buffers, every rank reduce-scatters the gradients, updates
  * its own slice with ncf_adam_range (elementwise Adam at step *step + 1; zeroes g; every row must be
@@ -279,6 +290,30 @@ int ncf_gather_rows(const float* table, const int64_t* idx, int64_t n, int32_t d
                     float* out, void* stream);
 int ncf_scatter_add_rows(float* table, const int64_t* idx, int64_t n, int32_t dim, int64_t rows,
                          const float* in, void* stream);
+
+/* The same exchange over peer memory on one NVLink node (no NCCL all-to-all, no split sizes on the host):
+ * every rank maps the others' buffers through CUDA IPC (ncf_peer_alloc / ncf_ipc_export / ncf_ipc_open) and
+ * passes arrays of `world` device addresses (entry r = rank r's buffer as seen from this device).
+ *   inbox        int64 [world][cap] per rank: entry (source r, j) = (local row << 32) | slot
+ *   inbox_count  int32 [world]      per rank: requests of source r
+ * ncf_shard_request (requester): writes one request per sample into the inbox of the owner of its item
+ *   (item % world) and then the per-owner counts; slot = the sample's position in the batch.  cursor:
+ *   int32[world] local scratch.  ncf_shard_mark_requests (owner): registers the requested rows in the item
+ *   side of the touched list (then ncf_adam_catchup).  ncf_shard_push_rows (owner): stores each requested
+ *   row of its item tables into the requester's receive buffers [cap, f] / [cap, d] at `slot`.
+ * ncf_shard_push_grads (requester): g_gmf[s] / g_mlp[s] (per-sample item-row gradients of the fused step)
+ *   are added (red.sys over NVLink) to row item[s] / world of the gradient tables of rank item[s] % world.
+ * The caller separates request | mark + catch-up + push rows | fused step + push grads | optimiser by rank
+ * barriers. */
+int ncf_shard_request(const int64_t* item, int64_t n, int32_t world, int32_t rank, int64_t cap, int64_t item_num,
+                      void* const* inbox_peers, void* const* inbox_count_peers, int32_t* cursor, void* stream);
+int ncf_shard_mark_requests(const NcfModel* m_host, const NcfGrads* g_host, const int64_t* inbox,
+                            const int32_t* inbox_count, int32_t world, int64_t cap, void* stream);
+int ncf_shard_push_rows(const NcfModel* m_host, const int64_t* inbox, const int32_t* inbox_count, int32_t world,
+                        int64_t cap, void* const* rows_gmf_peers, void* const* rows_mlp_peers, void* stream);
+int ncf_shard_push_grads(const int64_t* item, int64_t n, int32_t world, int64_t item_num, const float* g_gmf,
+                         const float* g_mlp, int32_t f, int32_t d, void* const* grad_gmf_peers,
+                         void* const* grad_mlp_peers, void* stream);
 
 /* ---- a11: leave-one-out evaluation --------------------------------------------------------------
  * Replaces metrics() (reference src/training/metrics.py:4-25).  scores is [n, C]; column 0 is the

@@ -61,8 +61,8 @@ SIGNATURES = {
     "ncf_profile_read": (C.c_int, [_vp, _vp, _i32, _i32]),
     "ncf_tower_param_count": (_i64, [_i32, _i32, _i32]),
     "ncf_csr_workspace_bytes": (_i64, [_i64, _i64]),
-    "ncf_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
-    "ncf_sample_neg": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i64, _u64, _u64, _vp, _vp]),
+    "ncf_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "ncf_sample_neg": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _u64, _u64, _vp, _vp]),
     "ncf_shuffle_epoch": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _u64, _u64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "ncf_forward_workspace_bytes": (_i64, [_P(NcfModel), _i64]),
     "ncf_forward": (C.c_int, [_P(NcfModel), _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
@@ -77,11 +77,16 @@ SIGNATURES = {
     "ncf_permute_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "ncf_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "ncf_scatter_add_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "ncf_shard_request": (C.c_int, [_vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "ncf_shard_mark_requests": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _i32, _i64, _vp]),
+    "ncf_shard_push_rows": (C.c_int, [_P(NcfModel), _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "ncf_shard_push_grads": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ncf_backward": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "ncf_mark_rows": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _i64, _vp]),
     "ncf_adam_prepare": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp, _vp, _i64, _vp]),
     "ncf_adam_step": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
     "ncf_adam_step_dense": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
+    "ncf_adam_step_dense_range": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _i64, _i64, _vp]),
     "ncf_adam_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, NcfAdamHyper, _vp]),
     "ncf_adam_finish_dense": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), _vp]),
     "ncf_adam_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, NcfAdamHyper, _vp]),

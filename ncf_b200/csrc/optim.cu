@@ -101,6 +101,7 @@ struct RowsParams {
   const int64_t* list[2];
   const int32_t* tcount;
   int64_t rows[2];
+  int64_t row0[2];  // first row of the all-rows modes (1, 3): rows [row0, row0 + rows) of each side
   const int64_t* step;
   int f, d, has_gmf, has_mlp;
   AdamConst c;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
       r = 0;
       last = 0;
       if (e < total) {
-        r = kList ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+        r = kList ? q.list[side][side ? e - n0 : e] : q.row0[side] + (side ? e - n0 : e);
         last = q.last[side][r];
       }
     };
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) adam_rows_kernel(const RowsParams q)
   }
   for (int64_t e = wid; e < total; e += nw) {
     const int side = e < n0 ? 0 : 1;
-    const int64_t r = kList ? q.list[side][side ? e - n0 : e] : (side ? e - n0 : e);
+    const int64_t r = kList ? q.list[side][side ? e - n0 : e] : q.row0[side] + (side ? e - n0 : e);
     const int32_t last = q.last[side][r];
     int gap;
     if (kStep) {
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const FlatParams q) {
   }
 }
 
+// (last_u / flag_u already point at the first user row of the range)
 __global__ void stamp_rows_kernel(int32_t* last_u, int32_t* flag_u, int64_t nu, int32_t* last_i, int32_t* flag_i,
                                   int64_t ni, const int64_t* step) {
   const int32_t t = (int32_t)(*step + 1);
@@ -528,20 +530,28 @@ int check_grads(const NcfModel* m, const NcfGrads* g) {
 }  // namespace
 
 static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
-                          void* stream, bool all_rows);
+                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi);
 
 extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
                              NcfAdamHyper h, void* stream) {
-  return adam_step_impl(m, g, s, h, stream, false);
+  return adam_step_impl(m, g, s, h, stream, false, 0, 0);
 }
 
 extern "C" int ncf_adam_step_dense(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
                                    NcfAdamHyper h, void* stream) {
-  return adam_step_impl(m, g, s, h, stream, true);
+  return adam_step_impl(m, g, s, h, stream, true, 0, m ? m->user_num : 0);
+}
+
+extern "C" int ncf_adam_step_dense_range(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
+                                         NcfAdamHyper h, int64_t user_lo, int64_t user_hi, void* stream) {
+  NCF_REQUIRE(m && user_lo >= 0 && user_lo <= user_hi && user_hi <= m->user_num,
+              "ncf_adam_step_dense_range: user range [%lld, %lld) outside the table", (long long)user_lo,
+              (long long)user_hi);
+  return adam_step_impl(m, g, s, h, stream, true, user_lo, user_hi);
 }
 
 static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
-                          void* stream, bool all_rows) {
+                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi) {
   int rc = ncf::validate_model(m);
   if (rc != NCF_OK) return rc;
   if ((rc = check_grads(m, g)) != NCF_OK) return rc;
@@ -553,22 +563,27 @@ static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamSta
   fill_rows(q, m, g, s);
   q.c = make_const(h);
   const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
+  if (all_rows) {  // users [user_lo, user_hi) (data-parallel ranks own a range of the user rows), every item
+    q.row0[0] = user_lo;
+    q.rows[0] = user_hi - user_lo;
+  }
   if (all_rows && vec) {
     FlatParams fp{};
     fp.step = q.step;
     fp.c = q.c;
     for (int side = 0; side < 2; ++side) {
+      const int64_t r0 = q.row0[side];
       if (q.has_gmf)
-        fp.tab[side] = FlatTable{q.p_gmf[side], q.m_gmf[side], q.v_gmf[side], q.g_gmf[side], q.last[side],
-                                 q.rows[side] * q.f / 4, q.f / 4};
+        fp.tab[side] = FlatTable{q.p_gmf[side] + r0 * q.f, q.m_gmf[side] + r0 * q.f, q.v_gmf[side] + r0 * q.f,
+                                 q.g_gmf[side] + r0 * q.f, q.last[side] + r0, q.rows[side] * q.f / 4, q.f / 4};
       if (q.has_mlp)
-        fp.tab[2 + side] = FlatTable{q.p_mlp[side], q.m_mlp[side], q.v_mlp[side], q.g_mlp[side], q.last[side],
-                                     q.rows[side] * q.d / 4, q.d / 4};
+        fp.tab[2 + side] = FlatTable{q.p_mlp[side] + r0 * q.d, q.m_mlp[side] + r0 * q.d, q.v_mlp[side] + r0 * q.d,
+                                     q.g_mlp[side] + r0 * q.d, q.last[side] + r0, q.rows[side] * q.d / 4, q.d / 4};
     }
     adam_flat_kernel<<<dim3(ncf::num_sms() * 4, 4), 256, 0, st>>>(fp);
     NCF_LAUNCH_CHECK("adam_flat_kernel");
-    stamp_rows_kernel<<<ncf::num_sms(), 256, 0, st>>>(q.last[0], q.flag[0], q.rows[0], q.last[1], q.flag[1], q.rows[1],
-                                                     q.step);
+    stamp_rows_kernel<<<ncf::num_sms(), 256, 0, st>>>(q.last[0] + q.row0[0], q.flag[0] + q.row0[0], q.rows[0], q.last[1],
+                                                     q.flag[1], q.rows[1], q.step);
     NCF_LAUNCH_CHECK("stamp_rows_kernel");
   } else if (all_rows) {
     adam_rows_kernel<3><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);

@@ -8,13 +8,15 @@ namespace {
 
 constexpr int kMaxAttempts = 1 << 16;  // a user who interacted with every item cannot loop forever
 
-__global__ void csr_count_kernel(const int64_t* __restrict__ pos_user, int64_t P, int64_t U,
-                                 unsigned long long* __restrict__ count, int* __restrict__ bad) {
+__global__ void csr_count_kernel(const int64_t* __restrict__ pos_user, const int64_t* __restrict__ pos_item, int64_t P,
+                                 int64_t U, unsigned long long* __restrict__ count, int* __restrict__ bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < P; i += stride) {
     int64_t u = pos_user[i];
-    if (u < 0 || u >= U) { *bad = 1; continue; }
+    const int64_t it = pos_item[i];
+    if (it < 0 || it > 0x7fffffffll) *bad = 1;   // columns are int32
+    if (u < 0 || u >= U) { *bad = 1; continue; }  // dropped from the CSR and reported through bad_flag
     atomicAdd(&count[u], 1ull);
   }
 }
@@ -58,8 +60,70 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ pos_user,
   }
 }
 
-// Rank sort inside each row: position of an item = number of smaller items in its row.  Equal
-// items (duplicate pairs) all write the same run of slots, so no slot is left unwritten.
+// ---- per-row sort of the columns ------------------------------------------------------------------------
+// csr_fill leaves every row's items in arrival order.  Rows are sorted in shared memory by a bitonic
+// network over the next power of two (padding = INT32_MAX, never written back): one WARP per row up to
+// kWarpRow items, one CTA per row up to kCtaRow items (128 KB).  Longer rows (more than 32 768 items of
+// one user) fall back to the rank sort below.  Duplicate pairs are kept.
+constexpr int kWarpRow = 256;
+constexpr int kCtaRow = 32768;
+
+template <bool WARP>
+__device__ __forceinline__ void bitonic_sort_shared(int32_t* a, int N, int tid, int nthreads) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < N; i += nthreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const int32_t x = a[i], y = a[ixj];
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      if (WARP) __syncwarp(); else __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) csr_sort_rows_warp_kernel(const int64_t* __restrict__ rowptr, int64_t U,
+                                                                 const int32_t* __restrict__ tmp, int32_t* __restrict__ col) {
+  __shared__ int32_t buf[8][kWarpRow];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t* a = buf[warp];
+  const int64_t nw = (int64_t)gridDim.x * 8;
+  for (int64_t u = (int64_t)blockIdx.x * 8 + warp; u < U; u += nw) {
+    const int64_t b = rowptr[u];
+    const int64_t n = rowptr[u + 1] - b;
+    if (n <= 0 || n > kWarpRow) continue;
+    int N = 1;
+    while (N < n) N <<= 1;
+    for (int i = lane; i < N; i += 32) a[i] = i < n ? tmp[b + i] : 0x7fffffff;
+    __syncwarp();
+    bitonic_sort_shared<true>(a, N, lane, 32);
+    for (int i = lane; i < n; i += 32) col[b + i] = a[i];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) csr_sort_rows_cta_kernel(const int64_t* __restrict__ rowptr, int64_t U,
+                                                                const int32_t* __restrict__ tmp, int32_t* __restrict__ col) {
+  extern __shared__ int32_t big[];
+  for (int64_t u = blockIdx.x; u < U; u += gridDim.x) {
+    const int64_t b = rowptr[u];
+    const int64_t n = rowptr[u + 1] - b;
+    if (n <= kWarpRow || n > kCtaRow) continue;   // uniform over the CTA
+    int N = 1;
+    while (N < n) N <<= 1;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) big[i] = i < n ? tmp[b + i] : 0x7fffffff;
+    __syncthreads();
+    bitonic_sort_shared<false>(big, N, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) col[b + i] = big[i];
+    __syncthreads();
+  }
+}
+
+// Rank sort inside a row (only rows longer than kCtaRow): position of an item = number of smaller items
+// in its row.  Equal items (duplicate pairs) all write the same run of slots, so no slot is left unwritten.
 __global__ void csr_rank_kernel(const int64_t* __restrict__ pos_user,
                                 const int64_t* __restrict__ pos_item, int64_t P, int64_t U,
                                 const int64_t* __restrict__ rowptr, const int32_t* __restrict__ tmp,
@@ -71,6 +135,7 @@ __global__ void csr_rank_kernel(const int64_t* __restrict__ pos_user,
     if (u < 0 || u >= U) continue;
     const int32_t it = (int32_t)pos_item[i];
     const int64_t b = rowptr[u], e = rowptr[u + 1];
+    if (e - b <= kCtaRow) continue;
     int64_t less = 0, equal = 0;
     for (int64_t j = b; j < e; ++j) {
       int32_t x = __ldg(&tmp[j]);
@@ -92,8 +157,11 @@ __device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ col, in
   return false;
 }
 
+// Out-of-range users and users whose every draw was rejected kMaxAttempts times (they interacted with
+// (nearly) every item; the reference loops forever there) get -1, which the training kernels report as
+// a bad index (NaN logit) instead of silently training on an observed pair.
 __global__ void sample_neg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                  const int64_t* __restrict__ pos_user, int64_t P, int64_t p_offset,
+                                  const int64_t* __restrict__ pos_user, int64_t P, int64_t p_offset, int64_t user_num,
                                   int num_ng, uint32_t item_num, uint32_t seed_lo, uint32_t seed_hi,
                                   uint32_t epoch, int64_t* __restrict__ out) {
   const int64_t total = P * num_ng;
@@ -102,11 +170,13 @@ __global__ void sample_neg_kernel(const int64_t* __restrict__ rowptr, const int3
   for (; g < total; g += stride) {
     const int64_t p = g / num_ng;
     const int64_t u = pos_user[p];
+    if (u < 0 || u >= user_num) { out[g] = -1; continue; }
     const int64_t lo = rowptr[u], hi = rowptr[u + 1];
     const uint64_t sid = (uint64_t)(p_offset * num_ng + g);
-    int32_t j = 0;
+    int32_t j = -1;
     Philox4 r = {0, 0, 0, 0};
-    for (int a = 0; a < kMaxAttempts; ++a) {
+    int a = 0;
+    for (; a < kMaxAttempts; ++a) {
       if ((a & 3) == 0)
         r = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(a >> 2), epoch, seed_lo,
                           seed_hi);
@@ -114,7 +184,7 @@ __global__ void sample_neg_kernel(const int64_t* __restrict__ rowptr, const int3
       j = (int32_t)__umulhi(w, item_num);
       if (!csr_contains(col, lo, hi, j)) break;
     }
-    out[g] = (int64_t)j;
+    out[g] = (a < kMaxAttempts) ? (int64_t)j : -1;
   }
 }
 
@@ -162,7 +232,7 @@ extern "C" int64_t ncf_csr_workspace_bytes(int64_t P, int64_t user_num) {
 }
 
 extern "C" int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, int64_t P,
-                             int64_t user_num, int64_t* rowptr, int32_t* col, void* workspace,
+                             int64_t user_num, int64_t* rowptr, int32_t* col, int32_t* bad_flag, void* workspace,
                              int64_t workspace_bytes, void* stream) {
   NCF_REQUIRE(P >= 0 && user_num > 0, "ncf_csr_build: bad sizes P=%lld U=%lld", (long long)P,
               (long long)user_num);
@@ -185,7 +255,7 @@ extern "C" int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, i
   NCF_CUDA(cudaMemsetAsync(bad, 0, 4, st));
   const int T = 256;
   if (P > 0) {
-    csr_count_kernel<<<grid_for(P, T), T, 0, st>>>(pos_user, P, user_num, count, bad);
+    csr_count_kernel<<<grid_for(P, T), T, 0, st>>>(pos_user, pos_item, P, user_num, count, bad);
     NCF_LAUNCH_CHECK("csr_count");
   }
   csr_scan_kernel<<<1, 1024, 0, st>>>(count, user_num, rowptr, cursor);
@@ -193,23 +263,33 @@ extern "C" int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, i
   if (P > 0) {
     csr_fill_kernel<<<grid_for(P, T), T, 0, st>>>(pos_user, pos_item, P, user_num, cursor, tmp);
     NCF_LAUNCH_CHECK("csr_fill");
+    csr_sort_rows_warp_kernel<<<grid_for(user_num * 32, T), T, 0, st>>>(rowptr, user_num, tmp, col);
+    NCF_LAUNCH_CHECK("csr_sort_rows_warp");
+    static bool attr_set = false;
+    if (!attr_set) {
+      NCF_CUDA(cudaFuncSetAttribute(csr_sort_rows_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaRow * 4));
+      attr_set = true;
+    }
+    csr_sort_rows_cta_kernel<<<ncf::num_sms(), T, kCtaRow * 4, st>>>(rowptr, user_num, tmp, col);
+    NCF_LAUNCH_CHECK("csr_sort_rows_cta");
     csr_rank_kernel<<<grid_for(P, T), T, 0, st>>>(pos_user, pos_item, P, user_num, rowptr, tmp, col);
     NCF_LAUNCH_CHECK("csr_rank");
   }
+  if (bad_flag != nullptr) NCF_CUDA(cudaMemcpyAsync(bad_flag, bad, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return NCF_OK;
 }
 
 extern "C" int ncf_sample_neg(const int64_t* rowptr, const int32_t* col, const int64_t* pos_user,
-                              int64_t P, int64_t p_offset, int32_t num_ng, int64_t item_num,
+                              int64_t P, int64_t p_offset, int64_t user_num, int32_t num_ng, int64_t item_num,
                               uint64_t seed, uint64_t epoch, int64_t* out_neg_item, void* stream) {
-  NCF_REQUIRE(P >= 0 && num_ng >= 0 && p_offset >= 0, "ncf_sample_neg: bad sizes");
+  NCF_REQUIRE(P >= 0 && num_ng >= 0 && p_offset >= 0 && user_num > 0, "ncf_sample_neg: bad sizes");
   NCF_REQUIRE(item_num > 0 && item_num <= 0x7fffffffLL, "ncf_sample_neg: item_num %lld out of range",
               (long long)item_num);
   if (P == 0 || num_ng == 0) return NCF_OK;
   NCF_REQUIRE(rowptr && col && pos_user && out_neg_item, "ncf_sample_neg: null pointer");
   const int T = 256;
   sample_neg_kernel<<<grid_for(P * num_ng, T), T, 0, (cudaStream_t)stream>>>(
-      rowptr, col, pos_user, P, p_offset, num_ng, (uint32_t)item_num, (uint32_t)seed,
+      rowptr, col, pos_user, P, p_offset, user_num, num_ng, (uint32_t)item_num, (uint32_t)seed,
       (uint32_t)(seed >> 32), (uint32_t)epoch, out_neg_item);
   NCF_LAUNCH_CHECK("sample_neg");
   return NCF_OK;

@@ -16,13 +16,22 @@ from ._lib import NcfAdamHyper, NcfAdamState, NcfGrads, NcfModel, check, current
 
 
 _ws_cache = {}
+_ws_pinned = []   # buffers whose address a captured CUDA graph has baked in: never freed
 
 
 def _workspace(device, nbytes: int):
-    """A per-device scratch buffer for inference calls (grown on demand, reused across calls on
-    the same stream; training owns its own workspace in FusedTrainStep)."""
+    """A per-device scratch buffer for eager inference calls (grown on demand, reused across calls on
+    the same stream).  A call made while a CUDA graph is being captured must not use it: the graph
+    bakes the pointer in and a later, larger request would replace (free) the buffer under the graph.
+    Captured calls therefore get a buffer of their own that stays alive for the process lifetime;
+    anything that is captured routinely (FusedTrainStep's teacher forward) passes an explicit
+    `workspace=` it owns instead."""
     if nbytes <= 0:
         return None
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_pinned.append(buf)
+        return buf
     key = (device.type, device.index)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -73,8 +82,10 @@ def model_struct(model_type: int, factor_num: int, num_layers: int, user_num: in
 
 
 # ---- a1 -----------------------------------------------------------------------------------------
-def csr_build(pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int):
-    """Sorted-column CSR of the observed pairs: (rowptr int64[U+1], col int32[P])."""
+def csr_build(pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int, validate: bool = True):
+    """Sorted-column CSR of the observed pairs: (rowptr int64[U+1], col int32[P]).  `validate` reads the
+    library's bad-index flag back (one host sync; building the CSR is a once-per-dataset step) and raises
+    on pairs outside the table, like the reference's dok_matrix fill does (IndexError)."""
     lib = _lib.load()
     P = pos_user.numel()
     dev = pos_user.device
@@ -82,9 +93,12 @@ def csr_build(pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int):
     col = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
     ws_bytes = lib.ncf_csr_workspace_bytes(P, user_num)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
     check(lib.ncf_csr_build(ptr(_i64(pos_user, "pos_user")), ptr(_i64(pos_item, "pos_item")), P,
-                            user_num, ptr(rowptr), ptr(col), ptr(ws), ws_bytes, current_stream()),
+                            user_num, ptr(rowptr), ptr(col), ptr(bad), ptr(ws), ws_bytes, current_stream()),
           "ncf_csr_build")
+    if validate and int(bad.item()) != 0:
+        raise _lib.NcfError(f"csr_build: a (user, item) pair lies outside the table (user_num={user_num})")
     return rowptr, col[:P]
 
 
@@ -99,7 +113,7 @@ def sample_neg(rowptr, col, pos_user, num_ng: int, item_num: int, seed: int, epo
         raise _lib.NcfError("sample_neg: out too small")
     colp = col if col.numel() else torch.zeros(1, dtype=torch.int32, device=pos_user.device)
     check(lib.ncf_sample_neg(ptr(_i64(rowptr, "rowptr")), ptr(colp), ptr(_i64(pos_user, "pos_user")),
-                             P, p_offset, num_ng, item_num, seed, epoch, ptr(_i64(out, "out")),
+                             P, p_offset, rowptr.numel() - 1, num_ng, item_num, seed, epoch, ptr(_i64(out, "out")),
                              current_stream()), "ncf_sample_neg")
     return out
 
@@ -118,8 +132,17 @@ def shuffle_epoch(pos_user, pos_item, neg_item, num_ng: int, seed: int, epoch: i
 
 
 # ---- a6 -----------------------------------------------------------------------------------------
+def forward_workspace_bytes(m: NcfModel, B: int) -> int:
+    n = int(_lib.load().ncf_forward_workspace_bytes(C.byref(m), B))
+    if n < 0:
+        raise _lib.NcfError("ncf_forward_workspace_bytes: bad model")
+    return n
+
+
 def forward(m: NcfModel, user: torch.Tensor, item: torch.Tensor,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`workspace`: caller-owned scratch of at least forward_workspace_bytes(m, B) bytes (required for
+    calls that end up in a CUDA graph); default = the shared per-device buffer."""
     lib = _lib.load()
     B = user.numel()
     if item.numel() != B:
@@ -129,7 +152,13 @@ def forward(m: NcfModel, user: torch.Tensor, item: torch.Tensor,
     ws_bytes = int(lib.ncf_forward_workspace_bytes(C.byref(m), B))
     if ws_bytes < 0:
         raise _lib.NcfError("ncf_forward_workspace_bytes: bad model")
-    ws = _workspace(user.device, ws_bytes)
+    if workspace is not None:
+        if workspace.numel() * workspace.element_size() < ws_bytes:
+            raise _lib.NcfError(f"forward: workspace of {workspace.numel() * workspace.element_size()} bytes "
+                                f"is smaller than the {ws_bytes} needed")
+        ws = workspace
+    else:
+        ws = _workspace(user.device, ws_bytes)
     check(lib.ncf_forward(C.byref(m), ptr(_i64(user, "user")), ptr(_i64(item, "item")), B,
                           ptr(_f32(out, "logits")), ptr(ws) if ws is not None else None, ws_bytes,
                           current_stream()), "ncf_forward")
@@ -170,8 +199,10 @@ class GradBuffers:
         f, d = factor_num, factor_num << (num_layers - 1)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
         gmf, mlp = model_type != _lib.NCF_MLP, model_type != _lib.NCF_GMF
-        shapes = [(user_num, f) if gmf else None, (item_num, f) if gmf else None,
-                  (user_num, d) if mlp else None, (item_num, d) if mlp else None,
+        # flat layout [user GMF | user MLP | item GMF | item MLP | tower]: the replicated part of a
+        # user-partitioned data-parallel step (items + tower) is one contiguous tail -> one all-reduce
+        shapes = [(user_num, f) if gmf else None, (user_num, d) if mlp else None,
+                  (item_num, f) if gmf else None, (item_num, d) if mlp else None,
                   (tower_param_count(model_type, factor_num, num_layers),)]
         sizes = [0 if s is None else (s[0] * s[1] if len(s) == 2 else s[0]) for s in shapes]
         sizes = [(n + 3) // 4 * 4 for n in sizes]  # keep every piece 16-byte aligned
@@ -181,6 +212,7 @@ class GradBuffers:
             numel = 0 if s is None else (s[0] * s[1] if len(s) == 2 else s[0])
             pieces.append(None if s is None else flat[off:off + numel].view(*s))
             off += n
+        pieces = [pieces[0], pieces[2], pieces[1], pieces[3], pieces[4]]   # field order of the dataclass
         return GradBuffers(
             *pieces, z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
             z(min(capacity, user_num), dt=torch.int64), z(min(capacity, item_num), dt=torch.int64),
@@ -305,6 +337,14 @@ def adam_step_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, be
           "ncf_adam_step_dense")
 
 
+def adam_step_dense_range(m: NcfModel, g: NcfGrads, s: NcfAdamState, user_lo: int, user_hi: int, lr,
+                          beta1=0.9, beta2=0.999, eps=1e-8):
+    """The all-rows Adam step over user rows [user_lo, user_hi) and every item row."""
+    check(_lib.load().ncf_adam_step_dense_range(C.byref(m), C.byref(g), C.byref(s),
+                                                NcfAdamHyper(lr, beta1, beta2, eps), int(user_lo), int(user_hi),
+                                                current_stream()), "ncf_adam_step_dense_range")
+
+
 def adam_range(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, step: torch.Tensor,
                lr, beta1=0.9, beta2=0.999, eps=1e-8):
     """Elementwise Adam step on flat fp32 slices (optimiser sharding in data-parallel training)."""
@@ -324,17 +364,19 @@ def adam_p2p(grad_ptrs, param_ptrs, m: torch.Tensor, v: torch.Tensor, lo: int, r
 
 
 class PeerBuffer:
-    """Zero-filled fp32 device buffer in an allocation of its own (ncf_peer_alloc), so that it can be
+    """Zero-filled device buffer in an allocation of its own (ncf_peer_alloc), so that it can be
     exported to the other ranks of the node through CUDA IPC.  `.tensor` aliases the memory."""
+    _TYPESTR = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4"}
 
-    def __init__(self, numel: int, device: torch.device):
-        self.numel, self.device = int(numel), device
+    def __init__(self, numel: int, device: torch.device, dtype: torch.dtype = torch.float32):
+        self.numel, self.device, self.dtype = int(numel), device, dtype
+        itemsize = torch.empty(0, dtype=dtype).element_size()
         out = C.c_void_p()
         with torch.cuda.device(device):
-            check(_lib.load().ncf_peer_alloc(self.numel * 4, C.byref(out)), "ncf_peer_alloc")
+            check(_lib.load().ncf_peer_alloc(max(self.numel, 1) * itemsize, C.byref(out)), "ncf_peer_alloc")
         self.address = out.value
-        self.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": "<f4", "data": (self.address, False),
-                                         "version": 2, "strides": None}
+        self.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": self._TYPESTR[dtype],
+                                         "data": (self.address, False), "version": 2, "strides": None}
         self.tensor = torch.as_tensor(self, device=device)   # keeps a reference to self
         self._peers = []
 
@@ -418,11 +460,13 @@ def eval_users(m: NcfModel, users: torch.Tensor, cands: torch.Tensor, k: int):
 
 # ---- (e) row-sharded tables -------------------------------------------------------------------------------
 def train_step_grads_norm(m: NcfModel, g: NcfGrads, user, item, label, B_norm: int,
-                          loss_accum: torch.Tensor, workspace: torch.Tensor) -> None:
+                          loss_accum: torch.Tensor, workspace: torch.Tensor, teacher_logits=None,
+                          alpha: float = 1.0) -> None:
     """Fused step whose loss mean runs over B_norm >= len(user) samples (a slice of a global batch)."""
     check(_lib.load().ncf_train_step_grads_norm(
         C.byref(m), C.byref(g), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
-        ptr(_f32(label, "label")), None, 1.0, user.numel(), int(B_norm), ptr(loss_accum), None,
+        ptr(_f32(label, "label")), ptr(teacher_logits) if teacher_logits is not None else None, alpha,
+        user.numel(), int(B_norm), ptr(loss_accum), None,
         ptr(workspace), workspace.numel() * workspace.element_size(), current_stream()),
         "ncf_train_step_grads_norm")
 
@@ -471,3 +515,38 @@ def scatter_add_rows(table: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor)
     check(_lib.load().ncf_scatter_add_rows(ptr(_f32(table, "table")), ptr(_i64(idx, "idx")), idx.numel(),
                                            table.shape[1], table.shape[0], ptr(_f32(rows, "rows")),
                                            current_stream()), "ncf_scatter_add_rows")
+
+
+def _ptr_array(addresses):
+    return (C.c_void_p * len(addresses))(*addresses)
+
+
+def shard_request(item: torch.Tensor, world: int, rank: int, cap: int, item_num: int, inbox_ptrs, count_ptrs,
+                  cursor: torch.Tensor) -> None:
+    check(_lib.load().ncf_shard_request(ptr(_i64(item, "item")) if item.numel() else None, item.numel(), world, rank,
+                                        cap, item_num, _ptr_array(inbox_ptrs), _ptr_array(count_ptrs), ptr(cursor),
+                                        current_stream()), "ncf_shard_request")
+
+
+def shard_mark_requests(m: NcfModel, g: NcfGrads, inbox: torch.Tensor, inbox_count: torch.Tensor, world: int,
+                        cap: int) -> None:
+    check(_lib.load().ncf_shard_mark_requests(C.byref(m), C.byref(g), ptr(inbox), ptr(inbox_count), world, cap,
+                                              current_stream()), "ncf_shard_mark_requests")
+
+
+def shard_push_rows(m: NcfModel, inbox: torch.Tensor, inbox_count: torch.Tensor, world: int, cap: int,
+                    rows_gmf_ptrs, rows_mlp_ptrs) -> None:
+    check(_lib.load().ncf_shard_push_rows(C.byref(m), ptr(inbox), ptr(inbox_count), world, cap,
+                                          _ptr_array(rows_gmf_ptrs) if rows_gmf_ptrs else None,
+                                          _ptr_array(rows_mlp_ptrs) if rows_mlp_ptrs else None, current_stream()),
+          "ncf_shard_push_rows")
+
+
+def shard_push_grads(item: torch.Tensor, world: int, item_num: int, g_gmf, g_mlp, f: int, d: int, grad_gmf_ptrs,
+                     grad_mlp_ptrs) -> None:
+    check(_lib.load().ncf_shard_push_grads(ptr(_i64(item, "item")) if item.numel() else None, item.numel(), world,
+                                           item_num, ptr(g_gmf) if g_gmf is not None else None,
+                                           ptr(g_mlp) if g_mlp is not None else None, f, d,
+                                           _ptr_array(grad_gmf_ptrs) if grad_gmf_ptrs else None,
+                                           _ptr_array(grad_mlp_ptrs) if grad_mlp_ptrs else None, current_stream()),
+          "ncf_shard_push_grads")

@@ -47,10 +47,15 @@ class FusedTrainStep:
                                      dtype=torch.uint8, device=dev)
         self.teacher_logits = (torch.empty(self.max_batch, dtype=torch.float32, device=dev)
                                if teacher is not None else None)
+        self.teacher_workspace = None
         if teacher is not None:
             teacher.eval()
             for p in teacher.parameters():  # reference src/distillation/base.py:16-18
                 p.requires_grad = False
+            # the teacher forward is captured into CUDA graphs with the rest of the step, so its scratch
+            # must be a buffer this object owns (the shared inference workspace can be replaced later)
+            nb = ops.forward_workspace_bytes(teacher.abi_struct(), self.max_batch)
+            self.teacher_workspace = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
         self._dirty = False  # True while some rows lag behind the dense-Adam state
         # Adam over every row instead of the touched rows once a step touches this share of the tables
         # (expected distinct rows of a uniform batch; NCF_ADAM_DENSE=0/1 forces a mode)
@@ -84,7 +89,7 @@ class FusedTrainStep:
         t_logits = None
         if self.teacher is not None:
             t_logits = self.teacher_logits[:B]
-            ops.forward(self._tm, user, item, out=t_logits)
+            ops.forward(self._tm, user, item, out=t_logits, workspace=self.teacher_workspace)
         dense = self.optimizer == "adam" and self.dense_adam(B)
         if self.optimizer == "adam":
             # rows this batch reads must first catch up with the dense-Adam trajectory — unless every
@@ -138,8 +143,7 @@ class StepGraph:
         # a window captured while every row was current contains no catch-up for its first step
         self.assumes_current = ts.optimizer == "adam" and not ts._dirty
         self.graph = torch.cuda.CUDAGraph()
-        # Snapshot and restore the optimiser/parameter state around the warm-up and capture
-        # launches so that capturing does not advance training.
+        # capture only records the launches: parameters and optimiser state are not advanced by it
         torch.cuda.synchronize()
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())

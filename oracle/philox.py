@@ -88,6 +88,9 @@ def sample_neg(rowptr, col, pos_user, num_ng, item_num, seed, epoch, p_offset=0)
         pos = np.searchsorted(keys, q)
         hit = (pos < keys.shape[0]) & (keys[np.minimum(pos, keys.shape[0] - 1)] == q)
         pending = pending[hit]
+    out[pending] = -1   # every draw was an observed pair (the reference loops forever): reported, not trained on
+    bad = (users < 0) | (users >= rowptr.shape[0] - 1)
+    out[bad] = -1
     return out
 
 

@@ -1,6 +1,7 @@
 """Worker for tests/test_gpu_multi.py: row-sharded training on N ranks (tables and Adam state split
-by row, item rows and their gradients exchanged by all-to-all) must reproduce single-process
-training at the global batch."""
+by row, item rows and their gradients exchanged over peer memory or by NCCL all-to-all:
+NCF_SHARD_P2P=1/0) must reproduce single-process training at the global batch - with uneven shards, hot
+rows, rows that skip steps and a step in which one rank has no samples at all."""
 import json
 import os
 import sys
@@ -31,6 +32,7 @@ def main():
     for t in (2, 3):                                  # rows that skip steps -> lazy-Adam catch-up across ranks
         users[t] = np.where(users[t] < 40, users[t] + 40, users[t])
         items[t] = np.where(items[t] < 30, items[t] + 30, items[t])
+    users[4] = users[4] // world * world              # step 4: every sample belongs to rank 0's users
     labels = (rng.random((T, Bg)) < 0.3).astype(np.float32)
 
     torch.manual_seed(0)
@@ -44,7 +46,7 @@ def main():
     for t in range(T):
         mine = users[t] % world == rank               # sharding follows the data: my users' samples
         tr.step(torch.from_numpy(users[t][mine]).to(dev), torch.from_numpy(items[t][mine]).to(dev),
-                torch.from_numpy(labels[t][mine]).to(dev))
+                torch.from_numpy(labels[t][mine]).to(dev), global_batch=Bg)
     got = tr.gather_full_state()
     loss = tr.loss_accum.clone()
     dist.all_reduce(loss)
@@ -63,7 +65,7 @@ def main():
         worst = max(worst, (got[k] - b).abs().max().item() / scale)
     if rank == 0:
         print(json.dumps({"vs_single_process": worst, "loss_sharded": loss.item(),
-                          "loss_single": rts.loss_accum.item(), "world": world}))
+                          "loss_single": rts.loss_accum.item(), "world": world, "p2p": tr.p2p}))
     dist.destroy_process_group()
 
 

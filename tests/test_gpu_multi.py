@@ -13,15 +13,35 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_replicated_dp_two_gpus():
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tests" / "dp_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+def _run_dp(port, **env):
+    cmd = ["timeout", "280", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "dp_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stderr[-2000:]
-    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("variant", ["lazy", "teacher", "big"])
+def test_user_partitioned_dp_two_gpus(variant):
+    """Default layout: every rank owns a user range and trains on its users' samples; only the item-table
+    and tower gradients are all-reduced.  `big` runs the tcgen05 path with the all-rows optimiser."""
+    env = {"lazy": {}, "teacher": {"DP_TEACHER": "1"}, "big": {"DP_BIG": "1"}}[variant]
+    res = _run_dp(29515, NCF_DP_PARTITION="1", **env)
+    assert res["partitioned"] is True
+    assert res["divergence"] == 0.0          # items + tower identical everywhere, user rows from their owners
+    assert res["vs_single_process"] < 2e-4   # same trajectory as one process at the global batch
+    assert abs(res["loss_dp"] - res["loss_single"]) < 1e-5 * abs(res["loss_single"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("teacher", ["0", "1"])
+def test_replicated_dp_two_gpus(teacher):
+    res = _run_dp(29517, NCF_DP_PARTITION="0", DP_TEACHER=teacher)
+    assert res["partitioned"] is False
     assert res["divergence"] == 0.0          # NCCL all-reduce leaves identical gradients everywhere
     assert res["vs_single_process"] < 2e-4   # same trajectory as one process at the global batch
+    assert abs(res["loss_dp"] - res["loss_single"]) < 1e-5 * abs(res["loss_single"])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -53,11 +73,15 @@ def test_replicated_dp_p2p_exchange_two_gpus():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_row_sharded_two_gpus():
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_row_sharded_two_gpus(p2p):
+    """Row-sharded tables; item rows and row gradients travel over peer memory (p2p=1: request / push
+    kernels over CUDA-IPC mappings, no host sync) or by NCCL all-to-all (p2p=0)."""
+    cmd = ["timeout", "280", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29519", str(ROOT / "tests" / "shard_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, NCF_SHARD_P2P=p2p))
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["p2p"] is (p2p == "1")
     assert res["vs_single_process"] < 2e-4
     assert abs(res["loss_sharded"] - res["loss_single"]) < 1e-5 * abs(res["loss_single"])

@@ -339,6 +339,54 @@ def test_sampler_csr_shuffle_bit_exact():
     assert np.array_equal(ou[:512].cpu().numpy(), wu[1000:1512])
 
 
+def test_csr_long_rows_duplicates_and_bad_pairs():
+    """Row sort in shared memory: one warp per short row, one CTA per row of up to 32 768 items; duplicate
+    pairs are kept; pairs outside the table are reported (bad flag) and left out."""
+    from ncf_b200 import ops
+    from ncf_b200._lib import NcfError
+    rng = np.random.default_rng(5)
+    U, I = 40, 60000
+    pu = [np.full(5000, 3), np.full(300, 4), np.full(257, 5), np.full(256, 6), np.full(40000, 7),
+          rng.integers(8, U, 4000)]
+    pi = [rng.integers(0, I, 5000), rng.integers(0, 500, 300), rng.permutation(I)[:257], rng.permutation(I)[:256],
+          rng.integers(0, I, 40000), rng.integers(0, I, 4000)]            # user 7: longer than a CTA row
+    pu, pi = np.concatenate(pu).astype(np.int64), np.concatenate(pi).astype(np.int64)
+    order = rng.permutation(pu.shape[0])
+    pu, pi = pu[order], pi[order]
+    tu, ti = torch.from_numpy(pu).to(dev()), torch.from_numpy(pi).to(dev())
+    rowptr, col = ops.csr_build(tu, ti, U)
+    o_rowptr, o_col = oph.csr_build(pu, pi, U)
+    assert np.array_equal(rowptr.cpu().numpy(), o_rowptr)
+    assert np.array_equal(col.cpu().numpy(), o_col)
+    # bad pairs: user outside the table
+    bu = torch.cat([tu, torch.tensor([U + 3], device=dev())])
+    bi = torch.cat([ti, torch.tensor([1], device=dev())])
+    with pytest.raises(NcfError):
+        ops.csr_build(bu, bi, U)
+    rowptr2, col2 = ops.csr_build(bu, bi, U, validate=False)      # the bad pair is left out
+    assert np.array_equal(rowptr2.cpu().numpy(), o_rowptr) and np.array_equal(col2.cpu().numpy(), o_col)
+    # the sampler writes -1 for a positive whose user is outside the table instead of reading rowptr out of bounds
+    neg = ops.sample_neg(rowptr, col, bu, 2, I, seed=3, epoch=0)
+    want = oph.sample_neg(o_rowptr, o_col, np.concatenate([pu, [U + 3]]), 2, I, 3, 0)
+    assert np.array_equal(neg.cpu().numpy(), want) and (want[-2:] == -1).all() and (want[:-2] >= 0).all()
+
+
+def test_sampler_reports_a_user_without_any_legal_negative():
+    """A user who interacted with every item: the reference loops forever (datasets.py:60-62); the
+    kernel gives up after 65 536 draws and writes -1, which the training kernels turn into a NaN logit."""
+    from ncf_b200 import ops
+    U, I = 3, 4
+    pu = np.array([0, 0, 0, 0, 1, 2], dtype=np.int64)
+    pi = np.array([0, 1, 2, 3, 1, 2], dtype=np.int64)
+    tu, ti = torch.from_numpy(pu).to(dev()), torch.from_numpy(pi).to(dev())
+    rowptr, col = ops.csr_build(tu, ti, U)
+    neg = ops.sample_neg(rowptr, col, tu, 2, I, seed=9, epoch=1).cpu().numpy()
+    o_rowptr, o_col = oph.csr_build(pu, pi, U)
+    want = oph.sample_neg(o_rowptr, o_col, pu, 2, I, 9, 1)
+    assert np.array_equal(neg, want)
+    assert (neg[:8] == -1).all() and (neg[8:] >= 0).all()
+
+
 def test_empty_and_invalid_inputs():
     from ncf_b200 import ops
     from ncf_b200._lib import NcfError
