@@ -178,6 +178,25 @@ int ncf_forward(const NcfModel* m_host, const int64_t* user, const int64_t* item
  * Adds the batch loss to *loss_accum (double) and, if dlogit != NULL, writes dloss/dx. */
 int ncf_loss_grad(const float* logits, const float* label, const float* teacher_logits,
                   float alpha, int64_t B, double* loss_accum, float* dlogit, void* stream);
+/* The other distillation objectives of the reference (src/distillation/base.py:26-50, response.py:34-61 and
+ * the logit-level terms of feature.py:125-146 / attention.py:81-101): per-sample
+ *   w_task * BCE(x, y) + w_kd * KD(x, t),   KD = (x - t)^2 (kd_mode 0) or
+ *   KD = T^2 * (sigmoid(x/T) - sigmoid(t/T))^2 (kd_mode 1: BaseDistillation.knowledge_distillation_loss),
+ * both means over the batch.  *loss_accum += loss; dlogit (nullable) receives dloss/dlogit for ncf_backward. */
+int ncf_loss_grad_kd(const float* logits, const float* label, const float* teacher_logits, float w_task,
+                     float w_kd, float temperature, int32_t kd_mode, int64_t B, double* loss_accum,
+                     float* dlogit, void* stream);
+/* Feature matching (reference src/distillation/feature.py:56-67,83-123) on one of the two embedding-level
+ * features: kind 0 = gmf_features (E_uG[u] * E_iG[i]), kind 1 = mlp_input ([E_uM[u] ; E_iM[i]]).
+ * *loss_accum += weight * mse(adapter(student feature), teacher feature); the gradient is added to the
+ * student's embedding-gradient rows in g (the rows must have been registered by the step: ncf_mark_rows /
+ * ncf_adam_prepare).  adapter_w [teacher width, student width] / adapter_b are the fixed nn.Linear the
+ * reference creates when the widths differ (feature.py:36-46; never optimised, train_student.py:131);
+ * NULL = identity (equal widths).  The tower-level features (mlp_linear_k / mlp_relu_k) only match for
+ * equal architectures and are served by the autograd path (ncf_b200.distillation.FeatureDistillation). */
+int ncf_feature_kd(const NcfModel* student_host, const NcfModel* teacher_host, const NcfGrads* g_host,
+                   const int64_t* user, const int64_t* item, int64_t B, int32_t kind, const float* adapter_w,
+                   const float* adapter_b, float weight, double* loss_accum, void* stream);
 
 /* ---- a6+a7+a8+a9: fused training step (forward, loss, backward) --------------------------------
  * Replaces `prediction = model(user,item); loss = criterion(...); loss.backward()` (reference

@@ -67,6 +67,8 @@ SIGNATURES = {
     "ncf_forward_workspace_bytes": (_i64, [_P(NcfModel), _i64]),
     "ncf_forward": (C.c_int, [_P(NcfModel), _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "ncf_loss_grad": (C.c_int, [_vp, _vp, _vp, _fl, _i64, _vp, _vp, _vp]),
+    "ncf_loss_grad_kd": (C.c_int, [_vp, _vp, _vp, _fl, _fl, _fl, _i32, _i64, _vp, _vp, _vp]),
+    "ncf_feature_kd": (C.c_int, [_P(NcfModel), _P(NcfModel), _P(NcfGrads), _vp, _vp, _i64, _i32, _vp, _vp, _fl, _vp, _vp]),
     "ncf_train_workspace_bytes": (_i64, [_P(NcfModel), _i64]),
     "ncf_train_step_grads": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _vp, _fl, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ncf_train_step_grads_norm": (C.c_int, [_P(NcfModel), _P(NcfGrads), _vp, _vp, _vp, _vp, _fl, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),

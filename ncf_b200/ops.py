@@ -178,6 +178,28 @@ def loss_grad(logits, label, teacher_logits, alpha: float, loss_accum: torch.Ten
           "ncf_loss_grad")
 
 
+def loss_grad_kd(logits, label, teacher_logits, w_task: float, w_kd: float, temperature: float, kd_mode: int,
+                 loss_accum: torch.Tensor, dlogit: Optional[torch.Tensor]) -> None:
+    """w_task * BCE + w_kd * KD with KD = logit MSE (kd_mode 0) or T^2-scaled soft-target MSE (kd_mode 1)."""
+    if loss_accum.dtype != torch.float64:
+        raise _lib.NcfError("loss_accum must be float64")
+    check(_lib.load().ncf_loss_grad_kd(ptr(_f32(logits, "logits")), ptr(_f32(label, "label")),
+                                       ptr(teacher_logits) if teacher_logits is not None else None, w_task, w_kd,
+                                       temperature, kd_mode, logits.numel(), ptr(loss_accum),
+                                       ptr(dlogit) if dlogit is not None else None, current_stream()),
+          "ncf_loss_grad_kd")
+
+
+def feature_kd(student: NcfModel, teacher: NcfModel, g: NcfGrads, user, item, kind: int, adapter_w, adapter_b,
+               weight: float, loss_accum: torch.Tensor) -> None:
+    """Feature-matching term on gmf_features (kind 0) or mlp_input (kind 1): loss value + row gradients."""
+    check(_lib.load().ncf_feature_kd(C.byref(student), C.byref(teacher), C.byref(g), ptr(_i64(user, "user")),
+                                     ptr(_i64(item, "item")), user.numel(), kind,
+                                     ptr(adapter_w) if adapter_w is not None else None,
+                                     ptr(adapter_b) if adapter_b is not None else None, weight, ptr(loss_accum),
+                                     current_stream()), "ncf_feature_kd")
+
+
 # ---- gradient / optimiser state ---------------------------------------------------------------------
 @dataclass
 class GradBuffers:

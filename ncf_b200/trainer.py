@@ -22,7 +22,21 @@ from .models import NCF
 class FusedTrainStep:
     def __init__(self, model: NCF, optimizer: str = "adam", lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, max_batch: int = 256, teacher: Optional[NCF] = None,
-                 alpha: float = 0.5):
+                 alpha: float = 0.5, distillation=None):
+        """`teacher` + `alpha`: response (teacher-score) KD, evaluated in the fused kernel's epilogue.
+        `distillation`: any ncf_b200.distillation object (Response / SoftTarget / Feature / Attention /
+        Unified); its teacher, weights and adapters are taken from it.  Objectives other than the
+        response one run as forward -> ncf_loss_grad_kd -> ncf_backward (+ ncf_feature_kd)."""
+        self.kd = None
+        if distillation is not None:
+            if distillation.student_model is not model:
+                raise ValueError("distillation.student_model must be the model being trained")
+            spec = distillation.fused_spec()
+            teacher = distillation.teacher_model
+            if spec["kd_mode"] == 0 and not spec["features"]:
+                alpha = spec["w_task"]                    # plain response KD: the fused epilogue does it
+            else:
+                self.kd = spec
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise _lib.NcfError("FusedTrainStep needs the model on a CUDA device (no CPU path)")
@@ -47,6 +61,9 @@ class FusedTrainStep:
                                      dtype=torch.uint8, device=dev)
         self.teacher_logits = (torch.empty(self.max_batch, dtype=torch.float32, device=dev)
                                if teacher is not None else None)
+        if self.kd is not None:
+            self.student_logits = torch.empty(self.max_batch, dtype=torch.float32, device=dev)
+            self.dlogit = torch.empty(self.max_batch, dtype=torch.float32, device=dev)
         self.teacher_workspace = None
         if teacher is not None:
             teacher.eval()
@@ -99,8 +116,11 @@ class FusedTrainStep:
                                  self.betas[1], self.eps)
         else:
             ops.mark_rows(self._m, self._g, user, item)
-        ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
-                             self.loss_accum, self.workspace, logits_out)
+        if self.kd is None:
+            ops.train_step_grads(self._m, self._g, user, item, label, t_logits, self.alpha,
+                                 self.loss_accum, self.workspace, logits_out)
+        else:
+            self._kd_grads(user, item, label, t_logits, logits_out)
         if dense:
             ops.adam_step_dense(self._m, self._g, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
             self._dirty = False
@@ -110,6 +130,21 @@ class FusedTrainStep:
         else:
             ops.sgd_step(self._m, self._g, self.lr)
         self.num_steps += 1
+
+    def _kd_grads(self, user, item, label, t_logits, logits_out=None) -> None:
+        """Objectives the fused epilogue does not evaluate: student forward -> loss + dloss/dlogit
+        (ncf_loss_grad_kd) -> fused backward from that dlogit (ncf_backward) -> feature-matching terms
+        (ncf_feature_kd: loss value + row gradients on the embedding-level features)."""
+        kd, B = self.kd, user.numel()
+        x = logits_out if logits_out is not None else self.student_logits[:B]
+        ops.forward(self._m, user, item, out=x, workspace=self.workspace)
+        dl = self.dlogit[:B]
+        ops.loss_grad_kd(x, label, t_logits, kd["w_task"], kd["w_kd"], kd["temperature"], kd["kd_mode"],
+                         self.loss_accum, dl)
+        ops.backward(self._m, self._g, user, item, dl, self.workspace)
+        for ft in kd["features"]:
+            ops.feature_kd(self._m, self._tm, self._g, user, item, ft["kind"], ft["w"], ft["b"], ft["weight"],
+                           self.loss_accum)
 
     def flush(self) -> None:
         """Brings every embedding row to the dense-Adam state of the current step.  Must run

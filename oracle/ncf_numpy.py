@@ -83,10 +83,14 @@ def loss_and_dlogit(logits, label, teacher_logits=None, alpha=0.5):
     return F32(loss), d.astype(F32)
 
 
-def backward(params, user, item, model_type, dlogit):
+def backward(params, user, item, model_type, dlogit, dfeat=None):
     """Gradients autograd produces for `loss.backward()` (reference scripts/train_neumf.py:114):
     dense zero-initialised table gradients with the per-sample rows summed, and tower dW / db.
-    Returns a dict keyed like the state_dict (absent key = parameter unused by this model_type)."""
+    Returns a dict keyed like the state_dict (absent key = parameter unused by this model_type).
+    `dfeat`: optional {feature name: dloss/dfeature [B, width]} for the intermediate features of
+    FeatureDistillation.extract_features (reference src/distillation/feature.py:48-81): gmf_features,
+    mlp_input, mlp_linear_k (pre-activation of tower layer k), mlp_relu_k (its output)."""
+    dfeat = dfeat or {}
     L = num_layers_of(params)
     _, acts = forward(params, user, item, model_type, return_acts=True)
     f = params["embed_user_GMF.weight"].shape[1]
@@ -100,6 +104,8 @@ def backward(params, user, item, model_type, dlogit):
     if model_type != "MLP":
         gu, gi = acts["gu"].astype(np.float64), acts["gi"].astype(np.float64)
         dprod = dl[:, None] * pw[None, :f]
+        if "gmf_features" in dfeat:
+            dprod = dprod + dfeat["gmf_features"].astype(np.float64)
         for key, idx, val in (("embed_user_GMF.weight", user, dprod * gi),
                               ("embed_item_GMF.weight", item, dprod * gu)):
             gt = np.zeros(params[key].shape, dtype=np.float64)
@@ -108,14 +114,20 @@ def backward(params, user, item, model_type, dlogit):
         off = f
     if model_type != "GMF":
         hs = [h.astype(np.float64) for h in acts["h"]]
-        delta = dl[:, None] * pw[None, off:] * (hs[L] > 0)
+        dh = dl[:, None] * pw[None, off:]                      # dloss / d(relu output of the last layer)
         for k in range(L - 1, -1, -1):
+            if f"mlp_relu_{k}" in dfeat:
+                dh = dh + dfeat[f"mlp_relu_{k}"].astype(np.float64)
+            delta = dh * (hs[k + 1] > 0)                        # dloss / d(pre-activation of layer k)
+            if f"mlp_linear_{k}" in dfeat:
+                delta = delta + dfeat[f"mlp_linear_{k}"].astype(np.float64)
             w, _ = _lin(params, k)
             g[f"MLP_layers.{3 * k + 1}.weight"] = (delta.T @ hs[k]).astype(F32)
             g[f"MLP_layers.{3 * k + 1}.bias"] = delta.sum(0).astype(F32)
-            delta = delta @ w.astype(np.float64)
-            if k > 0:
-                delta = delta * (hs[k] > 0)
+            dh = delta @ w.astype(np.float64)
+        delta = dh
+        if "mlp_input" in dfeat:
+            delta = delta + dfeat["mlp_input"].astype(np.float64)
         d = params["embed_user_MLP.weight"].shape[1]
         for key, idx, val in (("embed_user_MLP.weight", user, delta[:, :d]),
                               ("embed_item_MLP.weight", item, delta[:, d:])):
@@ -123,6 +135,104 @@ def backward(params, user, item, model_type, dlogit):
             np.add.at(gt, idx, val)
             g[key] = gt.astype(F32)
     return g
+
+
+def kd_loss_and_dlogit(logits, label, teacher_logits, w_task, w_kd, temperature=1.0, kd_mode=0):
+    """w_task * BCE(x, y) + w_kd * KD(x, t), means over the batch; returns (loss, dloss/dx).
+    kd_mode 0: KD = mse(x, t)  (ResponseDistillation.knowledge_distillation_loss, response.py:28-32)
+    kd_mode 1: KD = T^2 * mse(sigmoid(x/T), sigmoid(t/T))  (BaseDistillation, base.py:26-33; also the soft
+    term of SoftTargetDistillation, response.py:48-60, and the response term of Feature- /
+    AttentionDistillation)."""
+    B = logits.shape[0]
+    x, y = logits.astype(np.float64), label.astype(np.float64)
+    sig = 1.0 / (1.0 + np.exp(-x))
+    loss = w_task * bce_with_logits(logits, label).mean()
+    d = w_task * (sig - y)
+    if teacher_logits is not None and w_kd != 0:
+        t = teacher_logits.astype(np.float64)
+        if kd_mode == 0:
+            loss += w_kd * ((x - t) ** 2).mean()
+            d = d + w_kd * 2.0 * (x - t)
+        else:
+            T = float(temperature)
+            ss, st = 1.0 / (1.0 + np.exp(-x / T)), 1.0 / (1.0 + np.exp(-t / T))
+            loss += w_kd * T * T * ((ss - st) ** 2).mean()
+            d = d + w_kd * T * T * 2.0 * (ss - st) * ss * (1.0 - ss) / T
+    return F32(loss), (d / B).astype(F32)
+
+
+def extract_features(params, user, item):
+    """FeatureDistillation.extract_features (reference src/distillation/feature.py:48-81) in numpy."""
+    _, acts = forward(params, user, item, "NeuMF-end", return_acts=True)
+    L = num_layers_of(params)
+    feats = {"gmf_features": (acts["gu"] * acts["gi"]).astype(F32), "mlp_input": acts["h"][0]}
+    x = acts["h"][0].astype(np.float64)
+    for k in range(L):
+        w, b = _lin(params, k)
+        z = x @ w.T.astype(np.float64) + b
+        feats[f"mlp_linear_{k}"] = z.astype(F32)
+        x = np.maximum(z, 0.0)
+        feats[f"mlp_relu_{k}"] = x.astype(F32)
+    return feats
+
+
+def feature_matching(student_params, teacher_params, user, item, adapters, beta):
+    """beta * FeatureDistillation.feature_matching_loss (feature.py:83-123) and its gradient with respect to
+    every matched student feature.  adapters: {feature name: (W [teacher width, student width], b)} for the
+    features whose widths differ; a feature with different widths and no adapter is skipped, like the
+    reference does.  Returns (beta * loss, {feature name: dloss/dfeature})."""
+    fs, ft = extract_features(student_params, user, item), extract_features(teacher_params, user, item)
+    matched = []
+    for key in ft:
+        if key not in fs:
+            continue
+        if ft[key].shape != fs[key].shape and key not in adapters:
+            continue
+        matched.append(key)
+    loss, dfeat = 0.0, {}
+    for key in matched:
+        s_, t_ = fs[key].astype(np.float64), ft[key].astype(np.float64)
+        if ft[key].shape != fs[key].shape:
+            W, b = (a.astype(np.float64) for a in adapters[key])
+            r = s_ @ W.T + b - t_
+            loss += (r ** 2).mean() / len(matched)
+            dfeat[key] = (beta / len(matched)) * 2.0 / r.size * (r @ W)
+        else:
+            r = s_ - t_
+            loss += (r ** 2).mean() / len(matched)
+            dfeat[key] = (beta / len(matched)) * 2.0 / r.size * r
+    return beta * loss, dfeat
+
+
+def attention_transfer(student_params, teacher_params, user, item):
+    """AttentionDistillation.attention_transfer_loss (reference src/distillation/attention.py:16-79): the
+    attention map is softmax over the batch of the L2 norm of L2-normalised feature rows, i.e. 1/B for every
+    row with a non-zero feature vector on either side, so the KL term is ~0 (fp32 rounding) and has zero
+    gradient.  Evaluated here literally."""
+    def amap(x):
+        x = x.astype(np.float64)
+        n = np.linalg.norm(x, axis=-1, keepdims=True)
+        xn = x / np.maximum(n, 1e-12)
+        a = np.linalg.norm(xn, axis=-1, keepdims=True)
+        e = np.exp(a - a.max())
+        return (e / e.sum(axis=0, keepdims=True)).reshape(-1)
+    fs, ft = extract_features(student_params, user, item), extract_features(teacher_params, user, item)
+    total = 0.0
+    for key in ("gmf_features", "mlp_input"):
+        t, s_ = amap(ft[key]) + 1e-8, amap(fs[key]) + 1e-8
+        t, s_ = t / t.sum(), s_ / s_.sum()
+        total += float((t * (np.log(t) - np.log(s_))).sum() / t.shape[0])      # F.kl_div(log s, t, 'batchmean')
+    return total / 2
+
+
+def metrics_at_k(params, model_type, users, cands, ks):
+    """HR@k / NDCG@k means for every k (reference scripts/evaluate_models.py:22-32 calls metrics() per k)."""
+    (_, _), scores = metrics(params, model_type, users, cands, 1)
+    out = {}
+    for k in ks:
+        HR, NDCG = metrics_from_scores(scores, cands, k)
+        out[k] = (float(np.mean(HR)), float(np.mean(NDCG)))
+    return out
 
 
 class DenseAdam:

@@ -59,12 +59,20 @@ def main():
         rts.step(users[t], items[t], labels[t])
     rts.flush()
     loss_ref = rts.pop_loss()
-    worst = 0.0
+    # `worst`: largest deviation relative to the tensor's largest entry.  `share_over`: share of elements
+    # beyond 2e-4.  On the tcgen05 path the three MMA-issuing warps accumulate in a run-dependent order,
+    # so a ReLU pre-activation within fp32 rounding of zero (a few samples per 10^4) may take the other
+    # branch in the other run: that sample's rows then differ by O(10 %) of one Adam step while every
+    # other element agrees - the large-batch test bounds the share instead of the maximum.
+    worst, over, total = 0.0, 0, 0
     for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):
         scale = max(b.abs().max().item(), 1e-30)
-        worst = max(worst, (a - b).abs().max().item() / scale)
+        d = (a - b).abs() / scale
+        worst = max(worst, d.max().item())
+        over += int((d > 2e-4).sum().item())
+        total += d.numel()
     if rank == 0:
-        print(json.dumps({"divergence": divergence, "vs_single_process": worst, "world": world,
+        print(json.dumps({"divergence": divergence, "vs_single_process": worst, "share_over": over / total, "world": world,
                           "partitioned": dp.partition_users, "loss_dp": loss_dp, "loss_single": loss_ref}))
     dist.destroy_process_group()
 

@@ -92,6 +92,62 @@ def test_training_step_invariants_at_full_batch(ml20m):
     assert all(torch.equal(snap[k], v) for k, v in model.state_dict().items())
 
 
+def test_step_at_config4_shape_matches_oracle():
+    """BASELINE configs[3] at its real shape against the oracle: NeuMF f=32 L=3 on 138 493 x 26 744 tables,
+    ONE batch of 65 536 samples (tcgen05 path, 512 tiles, every CTA walks 3-4 tiles): logits, loss and every
+    gradient buffer within 1e-5, then the weights after the Adam step.  Samples whose tower pre-activation
+    lies within fp32 rounding of the ReLU kink are left out of the batch (relu' there depends on the last
+    bit; two correct fp32 implementations may disagree): ~0.2 % of the draws."""
+    from ncf_b200 import _lib, ops
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep
+    from oracle import ncf_numpy as onp
+    from tests import test_gpu_umma as tu
+    from tests.util import assert_close, assert_close_adam
+    U, I, f, L, B = 138_493, 26_744, 32, 3, 65536
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev())
+    with torch.no_grad():
+        for lin in model.linears():
+            lin.bias.uniform_(-0.1, 0.1)
+        for k, p in model.named_parameters():      # larger embeddings: logits and gradients well away from 0
+            if k.startswith("embed_"):
+                p.mul_(10.0)
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    n = B + B // 50
+    u = rng.integers(0, U, n)
+    i = np.minimum((rng.random(n) ** 2 * I).astype(np.int64), I - 1)      # skewed items: many duplicate rows
+    u[:4096] = rng.integers(0, 64, 4096)                                   # hot users
+    keep = ~tu._near_relu_kink(params, u, i, L, tol=1e-5)
+    assert keep.sum() >= B, "too many near-kink samples"
+    u, i = u[keep][:B], i[keep][:B]
+    y = (rng.random(B) < 0.2).astype(np.float32)
+    ud, idd, yd = (torch.from_numpy(a).to(dev()) for a in (u, i, y))
+    ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B)
+    logits = torch.empty(B, device=dev())
+    # gradients first (the optimiser would consume them)
+    ops.mark_rows(ts._m, ts._g, ud, idd)
+    ops.train_step_grads(ts._m, ts._g, ud, idd, yd, None, 1.0, ts.loss_accum, ts.workspace, logits)
+    torch.cuda.synchronize()
+    assert _lib.load().ncf_last_tile_path() == 3, "the tcgen05 path did not run"
+    ref_logits = onp.forward(params, u, i, "NeuMF-end")
+    ref_loss, dl = onp.loss_and_dlogit(ref_logits, y)
+    ref = onp.backward(params, u, i, "NeuMF-end", dl)
+    assert_close(logits.cpu().numpy(), ref_logits, "logits")
+    assert abs(ts.pop_loss() - float(ref_loss)) <= 5e-6 * abs(float(ref_loss))
+    tu._check_grads(model, ts.grads, ref)
+    # the same batch through the optimiser (all-rows mode at this batch size), against dense Adam
+    ts.grads.flat.zero_()
+    ts.grads.user_flag.zero_(); ts.grads.item_flag.zero_(); ts.grads.touched_count.zero_()
+    ts.step(ud, idd, yd)
+    ts.flush()
+    opt = onp.DenseAdam(lr=1e-3)
+    opt.step(params, ref)
+    for k, want in params.items():
+        assert_close_adam(model.state_dict()[k].cpu().numpy(), want, f"after Adam: {k}")
+
+
 def test_eval_at_full_size_and_reference_call_path(ml20m):
     """138 493 users x 100 candidates in one call; HR is a function of the rank only; and
     `metrics(model, DataLoader(NCFData(test_data), batch_size=100), k)` — the reference call
