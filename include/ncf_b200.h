@@ -140,6 +140,39 @@ int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, int64_t P, i
                   int64_t* rowptr, int32_t* col, int32_t* bad_flag, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* ---- (f) data side: the reference's on-disk formats and its leave-one-out preprocessing -------------------
+ * Text: u.train.rating (`user<TAB>item` per line) and u.test.negative (`(user,pos)<TAB>neg1<TAB>...`, no
+ * trailing newline) as written by reference src/data/preprocessing.py:137-154 and read by load_all
+ * (src/data/datasets.py:9-36).  ncf_text_line_starts: positions of the first byte of every non-empty line
+ * (a byte after '\n', or byte 0, that is not '\n' / '\r'); *n_lines (device) receives their number; with
+ * line_start == NULL only the count is produced (call once to size the array, once to fill it).
+ * ncf_text_parse_ints: out[line, j] = j-th integer (maximal digit run, optional leading '-') of the line,
+ * j < K; *status (device) bit 0 = a line had fewer than K integers (missing ones are -1: the reference
+ * would silently misalign its users there), bit 1 = (exact != 0) a line had more than K. */
+int64_t ncf_text_workspace_bytes(int64_t nbytes);
+int ncf_text_line_starts(const uint8_t* text, int64_t nbytes, int64_t* line_start, int64_t cap, int64_t* n_lines,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int ncf_text_parse_ints(const uint8_t* text, int64_t nbytes, const int64_t* line_start, int64_t n_lines, int32_t K,
+                        int32_t exact, int64_t* out, int32_t* status, void* stream);
+/* LeaveOneOutPreprocessor.temporal_split (reference src/data/preprocessing.py:45-90): ratings sorted by
+ * (user, timestamp, position in the file); the last one of every user with at least two ratings goes to
+ * (test_user, test_item) [ordered by user], everything else to (train_user, train_item) in sorted order.
+ * totals (device int64[2]) = {n_train, n_test}; train_* need room for n entries, test_* for user_num.
+ * *bad_flag (device, nullable): 1 = a user id outside [0, user_num) or a timestamp outside [0, 2^32),
+ * 2 = a user with more than 16 384 ratings (the shared-memory row sort does not take it). */
+int64_t ncf_split_workspace_bytes(int64_t n, int64_t user_num);
+int ncf_leave_one_out_split(const int64_t* user, const int64_t* item, const int64_t* timestamp, int64_t n,
+                            int64_t user_num, int64_t* train_user, int64_t* train_item, int64_t* test_user,
+                            int64_t* test_item, int64_t* totals, int32_t* bad_flag, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+/* generate_test_negatives (reference src/data/preprocessing.py:92-135): for test row r, up to K DISTINCT
+ * items uniform over [0, num_items) that are not in row test_user[r] of the CSR (train and test items of the
+ * user), at most 10 K draws, written ascending into out[r, :] (unused slots -1); count[r] = how many.
+ * Draw a uses word a % 4 of Philox4x32-10(counter = {r (lo), r (hi), a / 4, 'NEGS'}, key = seed). */
+int ncf_eval_negatives(const int64_t* rowptr, const int32_t* col, const int64_t* test_user, int64_t n,
+                       int64_t user_num, int64_t num_items, int32_t K, uint64_t seed, int64_t* out, int32_t* count,
+                       void* stream);
+
 /* ---- a2: negative sampler ---------------------------------------------------------------
  * Replaces NCFData.ng_sample (reference src/data/datasets.py:53-69): for positive p and
  * t < num_ng, out_neg_item[p*num_ng + t] is drawn uniformly from [0, item_num) and redrawn

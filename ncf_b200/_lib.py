@@ -62,6 +62,12 @@ SIGNATURES = {
     "ncf_tower_param_count": (_i64, [_i32, _i32, _i32]),
     "ncf_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "ncf_csr_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "ncf_text_workspace_bytes": (_i64, [_i64]),
+    "ncf_text_line_starts": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "ncf_text_parse_ints": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "ncf_split_workspace_bytes": (_i64, [_i64, _i64]),
+    "ncf_leave_one_out_split": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "ncf_eval_negatives": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _u64, _vp, _vp, _vp]),
     "ncf_sample_neg": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _u64, _u64, _vp, _vp]),
     "ncf_shuffle_epoch": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _u64, _u64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "ncf_forward_workspace_bytes": (_i64, [_P(NcfModel), _i64]),

@@ -2,9 +2,11 @@
 backed by arrays and device kernels instead of Python lists and a dok_matrix.
 
   * load_all(test_num=100) -> (train_data, test_data, user_num, item_num, train_mat): the two files
-    are parsed vectorised (the reference loops in Python and `eval`s every line, :22-35);
-    train_data / test_data are int64 arrays of [user, item] rows (indexable like the reference's
-    list of lists), train_mat is a `TrainMatrix` answering `(u, j) in train_mat`.
+    are read as bytes, copied to the GPU and parsed there (ncf_text_line_starts / ncf_text_parse_ints:
+    a byte-parallel line index, then one thread per line) where the reference loops in Python and
+    `eval`s every line (:22-35); train_data / test_data are int64 arrays of [user, item] rows
+    (indexable like the reference's list of lists), train_mat is a `TrainMatrix` answering
+    `(u, j) in train_mat`.  `load_all_device()` keeps everything on the GPU for the training scripts.
   * NCFData(features, num_item, train_mat=None, num_ng=0, is_training=None).ng_sample() draws the
     negatives on the GPU (CSR rejection + Philox, ncf_sample_neg); `features_fill` / `labels_fill`
     keep the positives-then-negatives layout of datasets.py:65-69; `__len__` / `__getitem__` serve
@@ -72,12 +74,61 @@ def parse_test_negative(path) -> np.ndarray:
     return np.asarray(rows, dtype=np.int64).reshape(-1, 2)
 
 
-def load_all(test_num=100):
-    train_data = parse_train_rating(config.train_rating)
+def _file_to_device(path, device) -> torch.Tensor:
+    raw = np.fromfile(path, dtype=np.uint8)
+    return torch.from_numpy(raw).to(device) if raw.size else torch.empty(0, dtype=torch.uint8, device=device)
+
+
+def parse_train_rating_device(text: torch.Tensor) -> torch.Tensor:
+    """uint8 CUDA tensor of a u.train.rating file -> int64 [P, 2] (user, item) on the device."""
+    from . import ops
+    pairs, status = ops.text_parse_ints(text, 2, exact=False)     # further columns (rating, timestamp) are ignored
+    if status & 1:
+        raise _lib.NcfError("u.train.rating: a line holds fewer than two integers")
+    return pairs
+
+
+def parse_test_negative_device(text: torch.Tensor, test_num: int = 100):
+    """uint8 CUDA tensor of a u.test.negative file -> (users int64 [n], cands int64 [n, test_num]) with the
+    held-out item in column 0.  A line with another number of candidates is an error: the reference
+    silently shifts every later user in that case."""
+    from . import ops
+    vals, status = ops.text_parse_ints(text, 1 + test_num, exact=True)
+    if status:
+        raise _lib.NcfError(f"u.test.negative: every line must hold (user, item) + {test_num - 1} negatives "
+                            f"({'fewer' if status & 1 else 'more'} found on some line)")
+    return vals[:, 0].contiguous(), vals[:, 1:].contiguous()
+
+
+def load_all_device(device="cuda", test_num=100):
+    """The files of load_all(), parsed on the GPU and left there:
+    (train pairs int64 [P, 2], test users [n], test candidates [n, test_num], user_num, item_num)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.NcfError("load_all_device parses on the GPU; use load_all(host=True) for host-side tooling")
+    train = parse_train_rating_device(_file_to_device(config.train_rating, dev))
+    users, cands = parse_test_negative_device(_file_to_device(config.test_negative, dev), test_num)
+    mx = train.max(dim=0).values
+    return train, users, cands, int(mx[0]) + 1, int(mx[1]) + 1
+
+
+def load_all(test_num=100, host=False):
+    """Reference signature (src/data/datasets.py:9).  host=False (default): GPU ingestion, needs a CUDA
+    device.  host=True: the numpy parser, for host-only tooling and CPU tests of the file writers."""
+    if host:
+        train_data = parse_train_rating(config.train_rating)
+        test_data = parse_test_negative(config.test_negative)
+    else:
+        if not torch.cuda.is_available():
+            raise _lib.NcfError("load_all parses the data files on the GPU and no CUDA device is visible "
+                                "(load_all(host=True) is the host-side parser)")
+        train, users, cands, _, _ = load_all_device("cuda", test_num)
+        train_data = train.cpu().numpy()
+        C = cands.shape[1]
+        test_data = torch.stack([users[:, None].expand(-1, C), cands], 2).reshape(-1, 2).cpu().numpy()
     user_num = int(train_data[:, 0].max()) + 1
     item_num = int(train_data[:, 1].max()) + 1
     train_mat = TrainMatrix(train_data, user_num, item_num)
-    test_data = parse_test_negative(config.test_negative)
     return train_data, test_data, user_num, item_num, train_mat
 
 

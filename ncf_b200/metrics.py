@@ -43,6 +43,30 @@ def evaluate(model, users: torch.Tensor, cands: torch.Tensor, top_k: int) -> Eva
     return EvalResult(hit, rank, ndcg, topk, scores)
 
 
+def evaluate_top_k(model, users: torch.Tensor, cands: torch.Tensor, max_k: int = 10):
+    """HR@K and NDCG@K for every K = 1..max_k from ONE scoring + ranking pass: the rank of the held-out
+    item among its candidates decides every K at once (hit iff rank < K).  Replaces the `max_k` full
+    evaluation passes of reference scripts/evaluate_models.py:22-32 (`metrics(model, loader, k)` per k).
+    Returns (hr_at_k, ndcg_at_k): dicts {k: mean over users}, the reference function's return value."""
+    res = evaluate(model, users, cands, max_k)
+    rank = res.rank.cpu().numpy().astype(np.int64)          # -1 = not within the top max_k
+    gain = np.where(rank >= 0, 1.0 / np.log2(np.maximum(rank, 0) + 2.0), 0.0)
+    hr_at_k, ndcg_at_k = {}, {}
+    for k in range(1, max_k + 1):
+        hit = (rank >= 0) & (rank < k)
+        hr_at_k[k] = float(np.mean(hit.astype(np.float64)))
+        ndcg_at_k[k] = float(np.mean(np.where(hit, gain, 0.0)))
+    return hr_at_k, ndcg_at_k
+
+
+def evaluate_top_k_performance(model, test_loader, max_k=10):
+    """Drop-in for reference scripts/evaluate_models.py:22-32 (same name, arguments and return value)."""
+    device = next(model.parameters()).device
+    users, cands = _test_tensors(test_loader, device)
+    with torch.no_grad():
+        return evaluate_top_k(model, users, cands, max_k)
+
+
 def _test_tensors(test_loader, device):
     """Pulls (users [n], cands [n, C]) out of a reference-style test DataLoader / NCFData."""
     ds = getattr(test_loader, "dataset", test_loader)

@@ -102,6 +102,67 @@ def csr_build(pos_user: torch.Tensor, pos_item: torch.Tensor, user_num: int, val
     return rowptr, col[:P]
 
 
+# ---- (f) on-disk formats and preprocessing --------------------------------------------------------------
+def text_parse_ints(text: torch.Tensor, K: int, exact: bool = False):
+    """text: uint8 CUDA tensor holding a whole file.  Returns (values int64 [n_lines, K], status int):
+    the first K integers of every non-empty line (see ncf_text_parse_ints)."""
+    lib = _lib.load()
+    if text.dtype != torch.uint8:
+        raise _lib.NcfError("text must be a uint8 tensor")
+    dev, nbytes = text.device, text.numel()
+    n_lines = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = int(lib.ncf_text_workspace_bytes(nbytes))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    tp = ptr(text) if nbytes else None
+    check(lib.ncf_text_line_starts(tp, nbytes, None, 0, ptr(n_lines), ptr(ws), ws_bytes, current_stream()),
+          "ncf_text_line_starts")
+    n = int(n_lines.item())                                   # one host read: sizes the outputs
+    starts = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    check(lib.ncf_text_line_starts(tp, nbytes, ptr(starts), n, ptr(n_lines), ptr(ws), ws_bytes, current_stream()),
+          "ncf_text_line_starts")
+    out = torch.empty(n, K, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.ncf_text_parse_ints(tp, nbytes, ptr(starts), n, K, int(bool(exact)), ptr(out) if n else None, ptr(status),
+                                  current_stream()), "ncf_text_parse_ints")
+    return out, int(status.item())
+
+
+def leave_one_out_split(user: torch.Tensor, item: torch.Tensor, timestamp: torch.Tensor, user_num: int):
+    """-> (train [n_train, 2], test [n_test, 2]) int64 CUDA tensors, see ncf_leave_one_out_split."""
+    lib = _lib.load()
+    n, dev = user.numel(), user.device
+    tr_u = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    tr_i = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    te_u = torch.empty(user_num, dtype=torch.int64, device=dev)
+    te_i = torch.empty(user_num, dtype=torch.int64, device=dev)
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.ncf_split_workspace_bytes(n, user_num))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.ncf_leave_one_out_split(ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(timestamp, "timestamp")),
+                                      n, user_num, ptr(tr_u), ptr(tr_i), ptr(te_u), ptr(te_i), ptr(totals), ptr(bad),
+                                      ptr(ws), ws_bytes, current_stream()), "ncf_leave_one_out_split")
+    flag = int(bad.item())
+    if flag == 1:
+        raise _lib.NcfError("leave_one_out_split: user id outside [0, user_num) or timestamp outside [0, 2^32)")
+    if flag == 2:
+        raise _lib.NcfError("leave_one_out_split: a user has more than 16384 ratings")
+    n_train, n_test = (int(x) for x in totals.tolist())
+    return torch.stack([tr_u[:n_train], tr_i[:n_train]], 1), torch.stack([te_u[:n_test], te_i[:n_test]], 1)
+
+
+def eval_negatives(rowptr: torch.Tensor, col: torch.Tensor, test_user: torch.Tensor, num_items: int, K: int, seed: int):
+    """-> (negatives int64 [n, K] ascending with -1 padding, count int32 [n]), see ncf_eval_negatives."""
+    n, dev = test_user.numel(), test_user.device
+    out = torch.empty(n, K, dtype=torch.int64, device=dev)
+    cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    colp = col if col.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().ncf_eval_negatives(ptr(_i64(rowptr, "rowptr")), ptr(colp), ptr(_i64(test_user, "test_user")), n,
+                                         rowptr.numel() - 1, num_items, K, seed, ptr(out), ptr(cnt), current_stream()),
+          "ncf_eval_negatives")
+    return out, cnt
+
+
 # ---- a2 -----------------------------------------------------------------------------------------
 def sample_neg(rowptr, col, pos_user, num_ng: int, item_num: int, seed: int, epoch: int,
                p_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -35,13 +35,10 @@ def load_dataset(device, synthetic: Optional[str] = None):
         d = make_interactions(synthetic, device=device)
         train = torch.stack([d.pos_user, d.pos_item], 1)
         return train, d.test_users, d.test_cands, d.user_num, d.item_num, None
-    from .datasets import load_all
+    from .datasets import load_all_device
     from .config import config
-    train_data, test_data, user_num, item_num, train_mat = load_all()
-    C = config.test_num_ng + 1
-    test = torch.as_tensor(test_data, device=device).reshape(-1, C, 2)
-    return (torch.as_tensor(train_data, device=device), test[:, 0, 0].contiguous(),
-            test[:, :, 1].contiguous(), user_num, item_num, train_mat)
+    train, users, cands, user_num, item_num = load_all_device(device, config.test_num_ng + 1)
+    return train, users, cands, user_num, item_num, None
 
 
 def fit(model: NCF, train_pairs: torch.Tensor, test_users: torch.Tensor, test_cands: torch.Tensor,

@@ -272,6 +272,25 @@ def test_eval_matches_reference(name):
     assert abs(res.hit.float().mean().item() - z["HR"].mean()) <= 1.0 / s.shape[0]
 
 
+def test_top_k_sweep_from_one_pass_matches_reference():
+    """evaluate_top_k: HR@K / NDCG@K for K = 1..10 from one ranking pass == the reference's ten metrics()
+    passes (scripts/evaluate_models.py:22-32; fixture metrics_ksweep), also through the DataLoader call."""
+    import torch.utils.data as data
+    from ncf_b200.datasets import NCFData
+    from ncf_b200.metrics import evaluate_top_k, evaluate_top_k_performance
+    z, meta = load_golden("metrics_ksweep")
+    model = build_model(group(z, "init"), meta).eval()
+    users, cands = torch.from_numpy(z["users"]).to(dev()), torch.from_numpy(z["cands"]).to(dev())
+    with torch.no_grad():
+        hr, ndcg = evaluate_top_k(model, users, cands, 10)
+    assert [hr[k] for k in range(1, 11)] == z["hr_at_k"].tolist()
+    assert np.allclose([ndcg[k] for k in range(1, 11)], z["ndcg_at_k"], rtol=1e-12, atol=0)
+    pairs = np.stack([np.repeat(z["users"], meta["C"]), z["cands"].reshape(-1)], 1)
+    loader = data.DataLoader(NCFData(pairs, meta["I"], None, 0, False), batch_size=meta["C"], shuffle=False)
+    hr2, ndcg2 = evaluate_top_k_performance(model, loader, max_k=10)
+    assert hr2 == hr and ndcg2 == ndcg
+
+
 def test_eval_rank_edge_cases():
     from ncf_b200 import ops
     # ties: the lower candidate index wins, so an all-equal row ranks the held-out item first

@@ -205,6 +205,46 @@ def test_distillation_and_backward_entry_match_the_mma_path(monkeypatch, mode):
         assert_close(got[2][k], ref[2][k], k, rtol=2e-5)
 
 
+@pytest.mark.parametrize("mode", ["kd", "dlogit"])
+def test_distillation_and_backward_entry_match_the_oracle(monkeypatch, mode):
+    """The same two entries on the tcgen05 path against the ORACLE directly: response-KD loss and gradients
+    from onp.loss_and_dlogit(..., teacher, alpha) (reference src/distillation/base.py:40-50,
+    response.py:28-32), and ncf_backward from a supplied dloss/dlogit."""
+    from ncf_b200.models import NCF
+    torch.manual_seed(5)
+    rng = np.random.default_rng(6)
+    U, I, f, L, B = 400, 300, 32, 3, 1500
+    model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(tp.dev())
+    with torch.no_grad():
+        for lin in model.linears():
+            lin.bias.uniform_(-0.1, 0.1)
+    params = tp.state_np(model)
+    u = rng.integers(0, U, B + 64)
+    i = rng.integers(0, I, B + 64)
+    keep = ~_near_relu_kink(params, u, i, L)
+    u, i = u[keep][:B], i[keep][:B]
+    y = (rng.random(B) < 0.3).astype(np.float32)
+    t_np = rng.standard_normal(B).astype(np.float32)
+    ud, idd, yd = (torch.from_numpy(a).to(tp.dev()) for a in (u, i, y))
+    logits_ref = onp.forward(params, u, i, "NeuMF-end")
+    if mode == "kd":
+        loss_ref, dl = onp.loss_and_dlogit(logits_ref, y, t_np, 0.4)
+        got = _grads_on_path(monkeypatch, False, model, ud, idd, yd, torch.from_numpy(t_np).to(tp.dev()), 0.4)
+        assert abs(got[0] - float(loss_ref)) <= 5e-6 * abs(float(loss_ref))
+        assert_close(got[1], logits_ref, "logits")
+    else:
+        dl = (rng.standard_normal(B) / B).astype(np.float32)
+        got = _grads_on_path(monkeypatch, False, model, ud, idd, yd, None, 1.0, torch.from_numpy(dl).to(tp.dev()))
+    ref = onp.backward(params, u, i, "NeuMF-end", dl)
+
+    class _G:   # _check_grads reads attributes
+        pass
+    gb = _G()
+    for k, v in got[2].items():
+        setattr(gb, k, torch.from_numpy(v))
+    _check_grads(model, gb, ref)
+
+
 def test_tf32_mode_training_step_is_close(monkeypatch):
     """tower_math='tf32' through the fused kernel and the weight-gradient kernel (one MMA-issuing warp,
     no lo images): gradients within TF32 rounding of the fp32-parity mode."""

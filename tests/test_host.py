@@ -94,7 +94,7 @@ def test_data_files_round_trip(tmp_path, monkeypatch):
     assert not te.read_text().endswith("\n")
     monkeypatch.setattr(datasets.config, "train_rating", tr)
     monkeypatch.setattr(datasets.config, "test_negative", te)
-    train_data, test_data, user_num, item_num, train_mat = datasets.load_all()
+    train_data, test_data, user_num, item_num, train_mat = datasets.load_all(host=True)
     assert user_num == int(inter.pos_user.max()) + 1 and item_num == int(inter.pos_item.max()) + 1
     assert np.array_equal(train_data, torch.stack([inter.pos_user, inter.pos_item], 1).numpy())
     assert test_data.shape == (50 * 100, 2)
