@@ -76,8 +76,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML (a thread, every 1 ms) during the timed
-    region — the same fields as the nvidia-smi clocks line of B200_PROFILING.md."""
+    """SM clock and throttle reasons sampled through NVML (a thread, every 1 ms; an NVML query itself takes
+    a few ms) from the start of the device-resident timed region to the end of the end-to-end one (the GPU
+    is under load throughout: timed steps, per-phase passes, host-fed steps) — the same fields as the
+    nvidia-smi clocks line of B200_PROFILING.md."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
@@ -502,7 +504,6 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         one_step(k)
     e1.record()
     barrier()
-    clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * K * B / (ms_total * 1e-3)
     dense = ts.dense_adam(B * world)
@@ -640,6 +641,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     for k in range(W, W + K):
         e2e_step(k)
     barrier()
+    clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
     del hf

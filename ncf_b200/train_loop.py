@@ -45,10 +45,12 @@ def fit(model: NCF, train_pairs: torch.Tensor, test_users: torch.Tensor, test_ca
         *, epochs: int, batch_size: int, lr: float, num_ng: int, top_k: int,
         optimizer: str = "adam", teacher: Optional[NCF] = None, alpha: float = 0.5, seed: int = 0,
         on_epoch: Optional[Callable] = None, on_best: Optional[Callable] = None,
-        use_graph: bool = True) -> TrainResult:
+        use_graph: bool = True, distillation=None) -> TrainResult:
+    """`teacher` + `alpha`: response KD; `distillation`: any ncf_b200.distillation object (its teacher,
+    weights and adapters are used; reference scripts/train_student.py:96-127)."""
     device = next(model.parameters()).device
     ts = FusedTrainStep(model, optimizer=optimizer, lr=lr, max_batch=batch_size, teacher=teacher,
-                        alpha=alpha)
+                        alpha=alpha, distillation=distillation)
     stream = EpochStream(train_pairs[:, 0].contiguous(), train_pairs[:, 1].contiguous(),
                          model.user_num, model.item_num, num_ng, seed=seed)
     res = TrainResult()

@@ -51,9 +51,6 @@ def main(argv=None):
     p.add_argument("--synthetic", type=str, default=None)
     p.add_argument("--seed", type=int, default=0)
     args = p.parse_args(argv)
-    if args.distillation != "response":
-        raise SystemExit(f"--distillation {args.distillation}: only the response (teacher-score) strategy is "
-                         "implemented on the fused path")
     os.environ.setdefault("CUDA_VISIBLE_DEVICES", args.gpu)
     if not torch.cuda.is_available():
         raise SystemExit("ncf_b200 needs a CUDA device: there is no CPU fallback")
@@ -81,9 +78,24 @@ def main(argv=None):
             torch.save(m.state_dict(), path)
             print(f"Saved best model to {path}")
 
+    # reference scripts/train_student.py:96-127 (its fourth branch imports a class its own tree does not have)
+    from ncf_b200.distillation import (AttentionDistillation, FeatureDistillation, ResponseDistillation,
+                                       UnifiedDistillation)
+    if args.distillation == "response":
+        distillation = ResponseDistillation(teacher, student, temperature=args.temperature, alpha=args.alpha)
+    elif args.distillation == "feature":
+        distillation = FeatureDistillation(teacher, student, temperature=args.temperature, alpha=args.alpha,
+                                           beta=args.beta)
+    elif args.distillation == "attention":
+        distillation = AttentionDistillation(teacher, student, temperature=args.temperature, alpha=args.alpha,
+                                             gamma=args.gamma)
+    else:
+        distillation = UnifiedDistillation(teacher, student, temperature=args.temperature, alpha=args.alpha,
+                                           beta=args.beta, gamma=args.gamma)
+    distillation.to(device)
     res = fit(student, train, test_users, test_cands, epochs=args.epochs, batch_size=args.batch_size,
-              lr=args.lr, num_ng=args.num_ng, top_k=args.top_k, optimizer="adam", teacher=teacher,
-              alpha=args.alpha, seed=args.seed, on_epoch=on_epoch, on_best=on_best)
+              lr=args.lr, num_ng=args.num_ng, top_k=args.top_k, optimizer="adam", distillation=distillation,
+              seed=args.seed, on_epoch=on_epoch, on_best=on_best)
     print(f"End. Best epoch {res.best_epoch:03d}: HR = {res.best_hr:.3f}, NDCG = {res.best_ndcg:.3f}")
     return res
 

@@ -1,1 +1,1 @@
-from ncf_b200.distillation import ResponseDistillation  # noqa: F401
+from ncf_b200.distillation import ResponseDistillation, SoftTargetDistillation  # noqa: F401

@@ -1,0 +1,38 @@
+"""End-to-end quality parity (north star: "matches reference HR@10/NDCG@10 within tolerance"): the
+reference training loop (scripts/train_neumf.py:98-131) was run for 2 epochs on a seeded ML-100K-shaped
+synthetic set with the batches of the epoch stream (fixture quality_ml100k, oracle/make_golden_r2.py);
+`train_loop.fit` — GPU sampler, shuffle, fused steps in CUDA-graph windows, lazy Adam, batched
+evaluation — must land on the same per-epoch loss, HR@10 and NDCG@10."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close_adam, group, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_two_epochs_match_the_reference_loop(use_graph):
+    from ncf_b200.models import NCF
+    from ncf_b200.train_loop import fit
+    z, meta = load_golden("quality_ml100k")
+    dev = torch.device("cuda:0")
+    model = NCF(meta["U"], meta["I"], meta["f"], meta["L"], 0.0, "NeuMF-end")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in group(z, "init").items()})
+    model = model.to(dev)
+    train = torch.from_numpy(np.stack([z["pos_user"], z["pos_item"]], 1).astype(np.int64)).to(dev)
+    cands = torch.from_numpy(z["cands"].astype(np.int64)).to(dev)
+    users = torch.arange(meta["U"], device=dev)
+    res = fit(model, train, users, cands, epochs=meta["epochs"], batch_size=meta["B"], lr=meta["lr"],
+              num_ng=meta["num_ng"], top_k=meta["top_k"], seed=meta["seed"], use_graph=use_graph)
+    for got, want in zip(res.history, z["history"]):
+        assert abs(got["loss"] - want[0]) <= 2e-4 * want[0], (got, want)
+        assert abs(got["hr"] - want[1]) <= 0.005 and abs(got["ndcg"] - want[2]) <= 0.005, (got, want)
+    assert res.best_hr > 0.6                                     # far above chance (0.1): the comparison means something
+    if use_graph:   # the final weights themselves, 3870 Adam steps later
+        worst = 0.0
+        for k, want in group(z, "final").items():
+            a = model.state_dict()[k].cpu().numpy()
+            worst = max(worst, float(np.abs(a - want).max() / np.abs(want).max()))
+        assert worst <= 5e-3, worst
