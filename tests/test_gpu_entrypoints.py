@@ -67,8 +67,12 @@ def test_pretrain_then_neumf_pre_then_distil(workdir, capsys):
     assert re.search(r"000 - Loss: \d+\.\d{6}, HR: \d\.\d{3}, NDCG: \d\.\d{3}, Time: \d\d:\d\d:\d\d", out)
     assert (models / "student_NeuMF-end_best.pth").exists()
     assert st.best_hr > 0.15
-    with pytest.raises(SystemExit):
-        train_student.main(["--distillation", "unified", "--synthetic", "tiny"])
+    # the other strategies of reference scripts/train_student.py:96-127 run on the fused path as well
+    for strategy in ("feature", "attention", "unified"):
+        st = train_student.main(["--teacher_model", "NeuMF-end", "--epochs", "3", "--num_layers", "2", "--factor_num", "8",
+                                 "--synthetic", "tiny", "--batch_size", "256", "--lr", "0.005", "--distillation", strategy])
+        capsys.readouterr()
+        assert st.best_hr > 0.15, strategy
 
 
 def test_tf32_tower_mode_within_stated_tolerance():

@@ -98,7 +98,7 @@ def _oracle_case(model_type, f, L, B, U=700, I=500, seed=0, bad_rows=()):
     return model, g, ref, None
 
 
-def _check_grads(model, g, ref):
+def _check_grads(model, g, ref, tower_rtol=1e-5):
     """Same walk over the gradient buffers as tests/test_gpu_parity.py."""
     tables = {"embed_user_GMF.weight": g.g_user_gmf, "embed_item_GMF.weight": g.g_item_gmf,
               "embed_user_MLP.weight": g.g_user_mlp, "embed_item_MLP.weight": g.g_item_mlp}
@@ -114,7 +114,7 @@ def _check_grads(model, g, ref):
         n = sd[k].numel()
         piece = flat[off:off + n].reshape(tuple(sd[k].shape))
         off += n
-        assert_close(piece, ref[k], f"grad {k}")
+        assert_close(piece, ref[k], f"grad {k}", rtol=tower_rtol)
     assert off == flat.size
 
 
