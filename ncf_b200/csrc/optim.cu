@@ -330,8 +330,8 @@ __global__ void mark_side_kernel(const int64_t* __restrict__ rows, int64_t n, in
 }
 
 // ---- the all-rows step as a streaming kernel ------------------------------------------------------------
-// blockIdx.y = table (user GMF, item GMF, user MLP, item MLP); a thread owns float4s of the table taken as
-// one flat array, so the four streams p, m, v, g are read and written fully coalesced.  `last` is only
+// A thread owns float4s of the four tables (user GMF, item GMF, user MLP, item MLP) taken as one flat index
+// space, so the four streams p, m, v, g are read and written fully coalesced.  `last` is only
 // read here (both tables of a row need the same gap); stamp_rows_kernel sets it afterwards.
 struct FlatTable {
   float *p, *m, *v, *g;
@@ -362,15 +362,19 @@ __device__ __forceinline__ void replay_inline(float& p, float& m, float& v, int 
 }
 
 __global__ void __launch_bounds__(256) adam_flat_kernel(const FlatParams q) {
-  const FlatTable T = q.tab[blockIdx.y];
-  if (T.n4 == 0) return;
+  // One index space over the four tables, so that every CTA streams the same number of float4s whatever the
+  // table sizes are (one grid row per table left the CTAs of the small tables idle for most of the kernel).
+  const int64_t e1 = q.tab[0].n4, e2 = e1 + q.tab[1].n4, e3 = e2 + q.tab[2].n4, total = e3 + q.tab[3].n4;
   const int64_t t = *q.step + 1;
   const float c1t = bias_c1(q.c, (float)t), c2t = bias_c2(q.c, (float)t);
-  float4* P = reinterpret_cast<float4*>(T.p);
-  float4* M = reinterpret_cast<float4*>(T.m);
-  float4* V = reinterpret_cast<float4*>(T.v);
-  float4* G = reinterpret_cast<float4*>(T.g);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T.n4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    const int ti = j < e1 ? 0 : j < e2 ? 1 : j < e3 ? 2 : 3;
+    const FlatTable& T = q.tab[ti];
+    const int64_t i = j - (ti == 0 ? 0 : ti == 1 ? e1 : ti == 2 ? e2 : e3);
+    float4* P = reinterpret_cast<float4*>(T.p);
+    float4* M = reinterpret_cast<float4*>(T.m);
+    float4* V = reinterpret_cast<float4*>(T.v);
+    float4* G = reinterpret_cast<float4*>(T.g);
     float4 p4 = P[i], m4 = M[i], v4 = V[i];
     const float4 g4 = G[i];
     const int32_t last = __ldg(&T.last[i / T.q4]);
@@ -383,7 +387,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const FlatParams q) {
       adam_real_step(pp[k], mp[k], vp[k], gp[k], c1t, c2t, q.c);
     }
     P[i] = p4; M[i] = m4; V[i] = v4;
-    G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // rows the step did not touch hold zeros already: do not write them again (half of the rows at the bench shape)
+    if (g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -580,7 +585,7 @@ static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamSta
         fp.tab[2 + side] = FlatTable{q.p_mlp[side] + r0 * q.d, q.m_mlp[side] + r0 * q.d, q.v_mlp[side] + r0 * q.d,
                                      q.g_mlp[side] + r0 * q.d, q.last[side] + r0, q.rows[side] * q.d / 4, q.d / 4};
     }
-    adam_flat_kernel<<<dim3(ncf::num_sms() * 4, 4), 256, 0, st>>>(fp);
+    adam_flat_kernel<<<ncf::num_sms() * 16, 256, 0, st>>>(fp);
     NCF_LAUNCH_CHECK("adam_flat_kernel");
     stamp_rows_kernel<<<ncf::num_sms(), 256, 0, st>>>(q.last[0] + q.row0[0], q.flag[0] + q.row0[0], q.rows[0], q.last[1],
                                                      q.flag[1], q.rows[1], q.step);
