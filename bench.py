@@ -412,8 +412,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world, st["dp_partitioned"]),
         "e2e": {"value": st["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": 8,
                 "ms_per_step": st["e2e_ms"] / K,
-                "launch": "HostFedTrainer: cuda-graph step, next batch H2D overlapped" if world == 1 and not args.no_graph
-                else "eager (NCCL inside the step)",
+                "launch": st["e2e_launch"],
                 "note": "value's timer is CUDA events on the stream, e2e's is the host clock around the same number of "
                         "steps; the two agree within run-to-run noise when the copies are hidden"},
         "gpu_launches": st["launches_per_step"] * K,
@@ -576,6 +575,24 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
                 kernel_ms[key] = kernel_ms.get(key, 0.0) + ms[j] / K
         lib.ncf_profile_enable(0)
         tile_path = {0: "none", 1: "generic", 2: "mma.sync", 3: "tcgen05"}[lib.ncf_last_tile_path()]
+    # the data-parallel step in place (N>1): wall time between CUDA events around the real dp.step calls, next to the
+    # sum of the local phases above -> what the collective and the wait for the slowest rank add
+    dp_in_place = None
+    if dp is not None:
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tms = []
+        for k in range(K):
+            u, i, y = bufs[k & 1]
+            stream.fill(q0 + (W + k) * B, B, u, i, y)
+            d0.record()
+            dp.step(u, i, y)
+            d1.record()
+            torch.cuda.synchronize()           # every step starts with all ranks idle: no run-ahead skew
+            tms.append(d0.elapsed_time(d1))
+        dp_in_place = {"dp_step_ms_synchronised": max_over_ranks(sorted(tms)[len(tms) // 2]),
+                       "overlap": dp.comm_stream is not None,
+                       "note": "median over steps of one dp.step between CUDA events with a host sync after every step"}
     # the step's collective alone (N>1): the all-reduce of the replicated gradient tail
     nvlink = None
     if dp is not None:
@@ -603,17 +620,20 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     dl = torch.empty(B, dtype=torch.float32, device=dev)
     host_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-    # single GPU: ncf_b200.trainer.HostFedTrainer — the step over static device buffers is a CUDA graph
-    # and the next batch's H2D copies run on a copy stream while the current step computes; every step
-    # still copies its own inputs from pinned host memory and reads its loss back.  Multi-GPU steps
-    # contain NCCL calls and stay eager.
+    # ncf_b200.trainer.HostFedTrainer — the step over static device buffers is a CUDA graph (at N>1 with
+    # the step's NCCL all-reduce captured in it) and the next batch's H2D copies run on a copy stream while
+    # the current step computes; every step still copies its own inputs from pinned host memory and reads
+    # its loss back.
     hf = None
-    if dp is None and not args.no_graph:
+    graph_ok = dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0")
+    if graph_ok and not args.no_graph:
         from ncf_b200.trainer import HostFedTrainer
+        step_fn = ts.step if dp is None else dp.step
         for k in range(2):  # every kernel loaded before capture
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])
-            ts.step(du, di, dl)
-        hf = HostFedTrainer(ts, B)
+            step_fn(du, di, dl)
+        barrier()
+        hf = HostFedTrainer(ts, B, step_fn if dp is not None else None)   # at N>1 the all-reduce is captured too
         nb = W + K
         hf.prefetch(hu[sl(0)], hi[sl(0)], hl[sl(0)])
 
@@ -644,6 +664,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
+    used_graph = hf is not None
     del hf
 
     # ---- evaluation throughput (second half of the metric: eval users/s): every rank scores its own users ----
@@ -742,8 +763,11 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
                                   "frac": (4 * R * 7 + 24) * value / world / 1e9 / hbm_peak}
         roofline["eval"] = eval_info["roofline"]
         roofline["nvlink"] = nvlink
+        roofline["dp_in_place"] = dp_in_place
 
-    return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks,
+    e2e_launch = ("HostFedTrainer: cuda-graph step" + (" (NCCL all-reduce captured)" if dp is not None else "")
+                  + ", next batch H2D overlapped") if used_graph else "eager"
+    return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,
                 dp_partitioned=(dp.partition_users if dp is not None else True))
 

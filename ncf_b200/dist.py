@@ -111,6 +111,12 @@ class ReplicatedDataParallel:
         self.n_rows_flat = (g.g_tower.data_ptr() - g.flat.data_ptr()) // 4
         self.comm_stream, self.sharded = None, None
         if self.partition_users:
+            # the item-row gradients are complete when the tower kernel is (before the weight-gradient kernel on
+            # the tcgen05 path): their all-reduce runs on a side stream under that kernel, and only the small
+            # tower-gradient all-reduce is left on the critical path (NCF_DP_OVERLAP=0 turns it off)
+            if dev.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("NCF_DP_OVERLAP", "1") != "0" \
+                    and self.n_rows_flat > self.n_user_flat:
+                self.comm_stream = torch.cuda.Stream(device=dev)
             return
         # ---- fully replicated layout ----
         # the row gradients (all of the flat buffer but its tower tail) are reduced on a side stream as
@@ -171,7 +177,21 @@ class ReplicatedDataParallel:
             ops.train_step_grads_norm(ts._m, ts._g, user, item, label, B, ts.loss_accum, ts.workspace,
                                       teacher_logits=t_logits, alpha=alpha)
         # every rank holds (sum over its samples) / B: the global-mean gradient is the plain sum
-        dist.all_reduce(ts.grads.flat[self.n_user_flat:], op=dist.ReduceOp.SUM)
+        flat = ts.grads.flat
+        if self.comm_stream is not None and b > 0:
+            ops.wait_embedding_grads(self.comm_stream)           # comm stream: after this rank's tower kernel
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat[self.n_user_flat:self.n_rows_flat], op=dist.ReduceOp.SUM)   # item rows
+            dist.all_reduce(flat[self.n_rows_flat:], op=dist.ReduceOp.SUM)                       # tower, after wgrad
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        elif self.comm_stream is not None:    # a rank without samples this step: same two collectives, in the same order
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat[self.n_user_flat:self.n_rows_flat], op=dist.ReduceOp.SUM)
+            dist.all_reduce(flat[self.n_rows_flat:], op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            dist.all_reduce(flat[self.n_user_flat:], op=dist.ReduceOp.SUM)
         if dense:
             ops.adam_step_dense_range(ts._m, ts._g, ts._s, self.user_lo, self.user_hi, ts.lr, ts.betas[0],
                                       ts.betas[1], ts.eps)

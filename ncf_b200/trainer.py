@@ -161,16 +161,19 @@ class FusedTrainStep:
 
     # -- CUDA-graph window ----------------------------------------------------------------------
     def capture(self, users: torch.Tensor, items: torch.Tensor, labels: torch.Tensor,
-                batch: int) -> "StepGraph":
-        """Captures `len(users) // batch` consecutive steps over static window buffers."""
-        return StepGraph(self, users, items, labels, batch)
+                batch: int, step_fn=None) -> "StepGraph":
+        """Captures `len(users) // batch` consecutive steps over static window buffers.  `step_fn`: the
+        step to record instead of self.step — e.g. a data-parallel wrapper's step, whose NCCL
+        collectives are captured with the kernels."""
+        return StepGraph(self, users, items, labels, batch, step_fn)
 
 
 class StepGraph:
     """A CUDA graph of consecutive FusedTrainStep.step() calls over fixed window buffers
     (refilled in place by ncf_shuffle_epoch between replays)."""
 
-    def __init__(self, ts: FusedTrainStep, users, items, labels, batch: int):
+    def __init__(self, ts: FusedTrainStep, users, items, labels, batch: int, step_fn=None):
+        step_fn = step_fn or ts.step
         n = users.numel() // batch
         if n < 1:
             raise _lib.NcfError("window smaller than one batch")
@@ -182,11 +185,13 @@ class StepGraph:
         torch.cuda.synchronize()
         stream = torch.cuda.Stream()
         stream.wait_stream(torch.cuda.current_stream())
+        # thread-local capture mode: NCCL's watchdog thread may query events while this thread captures
+        mode = "thread_local" if (torch.distributed.is_available() and torch.distributed.is_initialized()) else "global"
         with torch.cuda.stream(stream):
-            self.graph.capture_begin()
+            self.graph.capture_begin(capture_error_mode=mode)
             for i in range(n):
                 sl = slice(i * batch, (i + 1) * batch)
-                ts.step(users[sl], items[sl], labels[sl])
+                step_fn(users[sl], items[sl], labels[sl])
             self.graph.capture_end()
         torch.cuda.current_stream().wait_stream(stream)
         ts.num_steps -= n  # capture records, it does not execute
@@ -213,7 +218,9 @@ class HostFedTrainer:
         for k in range(n): hf.prefetch(*b[k + 1]); loss = hf.step()
     """
 
-    def __init__(self, ts: FusedTrainStep, batch: int):
+    def __init__(self, ts: FusedTrainStep, batch: int, step_fn=None):
+        """`step_fn`: the step each graph records (default ts.step); a ReplicatedDataParallel.step makes this
+        the host-fed trainer of a data-parallel rank (every rank must then call launch() in lock step)."""
         dev = ts.device
         self.ts, self.batch = ts, batch
         self.bufs = [(torch.empty(batch, dtype=torch.int64, device=dev),
@@ -221,7 +228,7 @@ class HostFedTrainer:
                       torch.empty(batch, dtype=torch.float32, device=dev)) for _ in range(2)]
         for b in self.bufs:  # valid indices for the capture pass
             b[0].zero_(); b[1].zero_(); b[2].zero_()
-        self.graphs = [ts.capture(*b, batch) for b in self.bufs]
+        self.graphs = [ts.capture(*b, batch, step_fn) for b in self.bufs]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
