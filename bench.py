@@ -368,7 +368,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = measured_peaks()
-    K, W = args.steps, max(3, args.warmup)
+    K, W = args.steps, max(4, args.warmup)     # >= 4: two eager steps, then each of the two step graphs replayed once
 
     if args.workload == "big":
         res = row_sharded_run(dev, world, rank, K, W, args.tower_math, hbm_peak)
@@ -483,17 +483,27 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    step_fn = ts.step if dp is None else dp.step
+    graphs = [None, None]
+
     def one_step(k):
         u, i, y = bufs[k & 1]
         stream.fill(q0 + k * B, B, u, i, y)          # shuffle + batching of the reference DataLoader, on the device
-        if dp is None:
-            ts.step(u, i, y)
+        if graphs[k & 1] is not None:
+            graphs[k & 1].replay()                   # the step over this buffer as one CUDA-graph launch
         else:
-            dp.step(u, i, y)
+            step_fn(u, i, y)
 
     # ---- device-resident timing ------------------------------------------------------------------
+    # the first warm-up steps run eagerly (they load every kernel), then the step over each of the two
+    # batch buffers is captured once (at N>1 with its NCCL all-reduce) and replayed: two launches per
+    # step from the host (shuffle + graph) - the same windows-of-graphs scheme train_epoch uses
+    use_step_graph = not args.no_graph and (dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0"))
     for k in range(W):
         one_step(k)
+        if k == 1 and use_step_graph:
+            barrier()
+            graphs = [ts.capture(*bufs[j], B, step_fn if dp is not None else None) for j in range(2)]
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -507,6 +517,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     value = world * K * B / (ms_total * 1e-3)
     dense = ts.dense_adam(B * world)
     umma = B >= 8192 and f >= 32
+    # kernels per step (replayed from a CUDA graph or launched one by one, the same kernels):
     # shuffle_epoch + [mark, catch-up] + (images, tower, wgrad | split, tile) + (flat, stamp | rows) + tower Adam + finalize
     launches_per_step = 1 + (0 if dense else 2) + (3 if umma else 2) + (2 if dense else 1) + 2
     if dp is not None and not dp.partition_users and dp.sharded is not None:
@@ -625,10 +636,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # the current step computes; every step still copies its own inputs from pinned host memory and reads
     # its loss back.
     hf = None
-    graph_ok = dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0")
-    if graph_ok and not args.no_graph:
+    if use_step_graph:
         from ncf_b200.trainer import HostFedTrainer
-        step_fn = ts.step if dp is None else dp.step
         for k in range(2):  # every kernel loaded before capture
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])
             step_fn(du, di, dl)

@@ -111,10 +111,12 @@ class ReplicatedDataParallel:
         self.n_rows_flat = (g.g_tower.data_ptr() - g.flat.data_ptr()) // 4
         self.comm_stream, self.sharded = None, None
         if self.partition_users:
-            # the item-row gradients are complete when the tower kernel is (before the weight-gradient kernel on
-            # the tcgen05 path): their all-reduce runs on a side stream under that kernel, and only the small
-            # tower-gradient all-reduce is left on the critical path (NCF_DP_OVERLAP=0 turns it off)
-            if dev.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("NCF_DP_OVERLAP", "1") != "0" \
+            # opt-in (NCF_DP_OVERLAP=1): the item-row gradients are complete when the tower kernel is (before the
+            # weight-gradient kernel on the tcgen05 path), so their all-reduce can run on a side stream under that
+            # kernel.  Measured at N=2 on B200: the NCCL CTAs take SMs from the one-CTA-per-SM weight-gradient
+            # kernel - 0.433 vs 0.437 ms for a synchronised step, 0.477 vs 0.428 ms in a run-ahead loop - so it
+            # stays off by default.
+            if dev.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("NCF_DP_OVERLAP", "0") == "1" \
                     and self.n_rows_flat > self.n_user_flat:
                 self.comm_stream = torch.cuda.Stream(device=dev)
             return
