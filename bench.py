@@ -257,7 +257,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(workload, n_gpus, partitioned=True):
+def config_dict(workload, n_gpus, partitioned=True, tail=False):
     shape, f, L, B = WORKLOADS[workload]
     from ncf_b200.synth import SHAPES
     U, I, total, _ = SHAPES[shape]
@@ -267,7 +267,8 @@ def config_dict(workload, n_gpus, partitioned=True):
         par = "dp1"
     elif partitioned:
         par = (f"dp{n_gpus}: every rank owns 1/{n_gpus} of the users and trains on their samples; item tables + "
-               f"tower replicated, their gradients all-reduced")
+               f"tower replicated, " + ("reduced, stepped and broadcast by one kernel over peer memory (ncf_adam_p2p)"
+                                        if tail else "their gradients all-reduced (NCCL)"))
     else:
         par = f"dp{n_gpus}: fully replicated tables, gradient all-reduce" + (
             " (exchange inside the Adam kernel over peer memory)" if os.environ.get("NCF_DP_P2P") == "1" else "")
@@ -409,7 +410,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": st["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": st["ms_total"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world, st["dp_partitioned"]),
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, world, st["dp_partitioned"], st["dp_tail"]),
         "e2e": {"value": st["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": 8,
                 "ms_per_step": st["e2e_ms"] / K,
                 "launch": st["e2e_launch"],
@@ -508,9 +509,14 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # At N>1 the loop waits for the device every 4th step, as a loop that reads its loss every few steps does: with
+    # all eight ranks running ahead unsynchronised the NCCL steps were measured 8 % slower (0.543 vs 0.497 ms at N=8)
+    sync_every = int(os.environ.get("NCF_BENCH_SYNC_EVERY", "4" if world > 1 else "0"))
     e0.record()
     for k in range(W, W + K):
         one_step(k)
+        if sync_every and (k - W + 1) % sync_every == 0:
+            torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -522,6 +528,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     launches_per_step = 1 + (0 if dense else 2) + (3 if umma else 2) + (2 if dense else 1) + 2
     if dp is not None and not dp.partition_users and dp.sharded is not None:
         launches_per_step = 1 + 3 + 3       # images, tower, wgrad, adam_range (or adam_p2p), stamp, finalize
+    if dp is not None and dp.tail is not None:
+        launches_per_step = 1 + 3 + 1 + 3   # shuffle, images, tower, wgrad, adam_p2p, adam_flat (users), stamp, finalize
 
     # materialise the timed batches once more for the per-phase and end-to-end passes
     bu = torch.empty(need, dtype=torch.int64, device=dev)
@@ -548,9 +556,14 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         def phase_grads(u, i, y):
             ops.train_step_grads_norm(ts._m, ts._g, u, i, y, B_norm, ts.loss_accum, ts.workspace)
 
+        tail = dp.tail if dp is not None else None
+
         def phase_adam():
-            if dense:
-                ops.adam_step_dense_range(ts._m, ts._g, ts._s, u_lo, u_hi, ts.lr)
+            if dense:   # with the peer-memory tail the local part of the optimiser is the user tables only
+                ops.adam_step_dense_range(ts._m, ts._g, ts._s, u_lo, u_hi, ts.lr,
+                                          parts=ops.PART_USERS if tail is not None else 7)
+                if tail is not None:
+                    tail["g"].zero_()
             else:
                 ops.adam_step(ts._m, ts._g, ts._s, ts.lr)
 
@@ -604,9 +617,31 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         dp_in_place = {"dp_step_ms_synchronised": max_over_ranks(sorted(tms)[len(tms) // 2]),
                        "overlap": dp.comm_stream is not None,
                        "note": "median over steps of one dp.step between CUDA events with a host sync after every step"}
-    # the step's collective alone (N>1): the all-reduce of the replicated gradient tail
+    # the step's exchange alone (N>1): the replicated gradient tail [item GMF | item MLP | tower]
     nvlink = None
-    if dp is not None:
+    if dp is not None and dp.tail is not None:
+        # reduce + Adam + broadcast of the tail in one kernel over peer memory, between its two rank barriers
+        tl = dp.tail
+        m0, v0 = tl["m"].clone(), tl["v"].clone()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            dist.all_reduce(tl["flag"])
+            ops.adam_p2p(tl["gptrs"], tl["pptrs"], tl["m"], tl["v"], tl["lo"], rank, ts.state.step, 0.0, grad_scale=1.0)
+            dist.all_reduce(tl["flag"])
+        c1.record()
+        barrier()
+        tl["m"].copy_(m0); tl["v"].copy_(v0)           # lr = 0 left the parameters alone; restore the moments
+        ex_ms = max_over_ranks(c0.elapsed_time(c1) / 10)
+        per_bytes = tl["per"] * 4
+        wire = (world - 1) * per_bytes                  # gradient slices read from the peers = parameter slices written to them
+        nvlink = {"exchange": "ncf_adam_p2p: reduce + Adam + broadcast of [item GMF | item MLP | tower] over peer memory, "
+                              "two one-element all-reduces as rank barriers",
+                  "buffer_bytes": tl["g"].numel() * 4, "ms": ex_ms, "bytes_in_per_gpu": wire, "bytes_out_per_gpu": wire,
+                  "achieved_gbs": wire / (ex_ms * 1e-3) / 1e9, "peak_gbs_per_direction": NVLINK_GBS,
+                  "frac": wire / (ex_ms * 1e-3) / 1e9 / NVLINK_GBS, "share_of_step": ex_ms / (ms_total / K)}
+    elif dp is not None:
         buf = ts.grads.flat[dp.n_user_flat:] if dp.partition_users else ts.grads.flat
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -671,6 +706,13 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         e2e_step(k)
     barrier()
     clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
+    if world > 1:               # every rank watched its own GPU: keep the slowest one in view as well
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        mhz = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
+        clocks["all_ranks"] = {"sm_mhz_min_of_medians": min(mhz) if mhz else None,
+                               "sm_mhz_per_rank": [c["sm_mhz"] for c in allc],
+                               "reasons": sorted({r for c in allc for r in c["reasons"]})}
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
     used_graph = hf is not None
@@ -778,7 +820,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
                   + ", next batch H2D overlapped") if used_graph else "eager"
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,
-                dp_partitioned=(dp.partition_users if dp is not None else True))
+                dp_partitioned=(dp.partition_users if dp is not None else True),
+                dp_tail=(dp is not None and dp.tail is not None))
 
 
 def sampler_run(dev, hbm_peak):

@@ -293,9 +293,12 @@ int ncf_adam_step_dense(const NcfModel* m_host, const NcfGrads* g_host, const Nc
                         NcfAdamHyper h, void* stream);
 /* The all-rows step restricted to user rows [user_lo, user_hi) (and every item row): data-parallel
  * ranks that each train on the samples of their own range of users (new design) own
- * those user rows - the other user rows are never read or written on this rank. */
+ * those user rows - the other user rows are never read or written on this rank.  parts: mask of 1 (user
+ * tables), 2 (item tables), 4 (tower) = what this call updates; the rest was updated by another path of
+ * the same step (the peer-memory exchange ncf_adam_p2p for the replicated item tables and the tower).
+ * Every row of both sides is stamped as current and the step counter is incremented whatever parts is. */
 int ncf_adam_step_dense_range(const NcfModel* m_host, const NcfGrads* g_host, const NcfAdamState* s_host,
-                              NcfAdamHyper h, int64_t user_lo, int64_t user_hi, void* stream);
+                              NcfAdamHyper h, int64_t user_lo, int64_t user_hi, int32_t parts, void* stream);
 /* Optimiser sharding for replicated data parallelism (new design): with parameters,
  * gradients and moments laid out as flat buffers, every rank reduce-scatters the gradients, updates
  * its own slice with ncf_adam_range (elementwise Adam at step *step + 1; zeroes g; every row must be
@@ -308,12 +311,13 @@ int ncf_adam_finish_dense(const NcfModel* m_host, const NcfGrads* g_host, const 
 /* The same sharded step with the gradient exchange inside the kernel, for ranks on one NVLink node
  * (experimental, NCF_DP_P2P=1 in ncf_b200.dist): grad_bufs / param_bufs are HOST arrays of `world`
  * device pointers - entry r is rank r's flat gradient / parameter buffer, entry `rank` the caller's own,
- * the others mapped with ncf_ipc_open.  The caller owns elements [lo, lo + n): the kernel averages
- * that slice over every rank's gradients (peer loads), updates m / v (n elements, local) and stores the
+ * the others mapped with ncf_ipc_open.  The caller owns elements [lo, lo + n): the kernel sums that slice
+ * over every rank's gradients (peer loads) times grad_scale (1/world for rank-mean gradients, 1 when every
+ * rank already divided by the global batch), updates m / v (n elements, local) and stores the
  * new parameters into every rank's buffer (peer stores).  Bracket it with rank barriers: all gradients
  * complete before, all ranks done after (then zero the local gradient buffer). */
 int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_bufs, float* m, float* v, int64_t lo, int64_t n,
-                 int32_t world, int32_t rank, const int64_t* step, NcfAdamHyper h, void* stream);
+                 int32_t world, int32_t rank, float grad_scale, const int64_t* step, NcfAdamHyper h, void* stream);
 /* Buffers shared between ranks have to be allocations of their own (CUDA IPC exports whole
  * allocations): ncf_peer_alloc returns zero-filled device memory of the current device, the only
  * memory this library ever owns; ncf_ipc_export writes its 64-byte handle, which the peers turn into

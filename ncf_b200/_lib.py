@@ -94,10 +94,10 @@ SIGNATURES = {
     "ncf_adam_prepare": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp, _vp, _i64, _vp]),
     "ncf_adam_step": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
     "ncf_adam_step_dense": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _vp]),
-    "ncf_adam_step_dense_range": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _i64, _i64, _vp]),
+    "ncf_adam_step_dense_range": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), NcfAdamHyper, _i64, _i64, _i32, _vp]),
     "ncf_adam_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, NcfAdamHyper, _vp]),
     "ncf_adam_finish_dense": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), _vp]),
-    "ncf_adam_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, NcfAdamHyper, _vp]),
+    "ncf_adam_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _fl, _vp, NcfAdamHyper, _vp]),
     "ncf_peer_alloc": (C.c_int, [_i64, _vp]),
     "ncf_peer_free": (C.c_int, [_vp]),
     "ncf_ipc_export": (C.c_int, [_vp, _vp]),

@@ -534,8 +534,9 @@ int check_grads(const NcfModel* m, const NcfGrads* g) {
 
 }  // namespace
 
+constexpr int kPartUsers = 1, kPartItems = 2, kPartTower = 4, kPartAll = 7;
 static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
-                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi);
+                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi, int parts = kPartAll);
 
 extern "C" int ncf_adam_step(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
                              NcfAdamHyper h, void* stream) {
@@ -548,15 +549,16 @@ extern "C" int ncf_adam_step_dense(const NcfModel* m, const NcfGrads* g, const N
 }
 
 extern "C" int ncf_adam_step_dense_range(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s,
-                                         NcfAdamHyper h, int64_t user_lo, int64_t user_hi, void* stream) {
+                                         NcfAdamHyper h, int64_t user_lo, int64_t user_hi, int32_t parts, void* stream) {
   NCF_REQUIRE(m && user_lo >= 0 && user_lo <= user_hi && user_hi <= m->user_num,
               "ncf_adam_step_dense_range: user range [%lld, %lld) outside the table", (long long)user_lo,
               (long long)user_hi);
-  return adam_step_impl(m, g, s, h, stream, true, user_lo, user_hi);
+  NCF_REQUIRE(parts >= 0 && parts <= kPartAll, "ncf_adam_step_dense_range: parts must be a mask of 1 | 2 | 4");
+  return adam_step_impl(m, g, s, h, stream, true, user_lo, user_hi, parts);
 }
 
 static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamState* s, NcfAdamHyper h,
-                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi) {
+                          void* stream, bool all_rows, int64_t user_lo, int64_t user_hi, int parts) {
   int rc = ncf::validate_model(m);
   if (rc != NCF_OK) return rc;
   if ((rc = check_grads(m, g)) != NCF_OK) return rc;
@@ -577,6 +579,7 @@ static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamSta
     fp.step = q.step;
     fp.c = q.c;
     for (int side = 0; side < 2; ++side) {
+      if (!(parts & (side ? kPartItems : kPartUsers))) continue;   // that side was updated elsewhere (peer-memory step)
       const int64_t r0 = q.row0[side];
       if (q.has_gmf)
         fp.tab[side] = FlatTable{q.p_gmf[side] + r0 * q.f, q.m_gmf[side] + r0 * q.f, q.v_gmf[side] + r0 * q.f,
@@ -591,17 +594,20 @@ static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamSta
                                                      q.flag[1], q.rows[1], q.step);
     NCF_LAUNCH_CHECK("stamp_rows_kernel");
   } else if (all_rows) {
+    NCF_REQUIRE(parts == kPartAll, "ncf_adam_step_dense_range: partial steps need row widths that are multiples of 4");
     adam_rows_kernel<3><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
     NCF_LAUNCH_CHECK("adam_rows_kernel");
   } else {
     adam_rows_kernel<0><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
     NCF_LAUNCH_CHECK("adam_rows_kernel");
   }
-  DenseParams dq{};
-  fill_dense(dq, m);
-  dq.g = g->g_tower; dq.m = s->m_tower; dq.v = s->v_tower; dq.step = s->step; dq.c = q.c;
-  adam_dense_kernel<<<dim3(32, dq.nseg), 256, 0, st>>>(dq);
-  NCF_LAUNCH_CHECK("adam_dense_kernel");
+  if (parts & kPartTower) {
+    DenseParams dq{};
+    fill_dense(dq, m);
+    dq.g = g->g_tower; dq.m = s->m_tower; dq.v = s->v_tower; dq.step = s->step; dq.c = q.c;
+    adam_dense_kernel<<<dim3(32, dq.nseg), 256, 0, st>>>(dq);
+    NCF_LAUNCH_CHECK("adam_dense_kernel");
+  }
   finalize_step_kernel<<<1, 1, 0, st>>>(s->step, g->touched_count);
   NCF_LAUNCH_CHECK("finalize_step_kernel");
   return NCF_OK;
@@ -727,8 +733,8 @@ extern "C" int ncf_adam_range(float* p, float* m, float* v, float* g, int64_t n,
 }
 
 extern "C" int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_bufs, float* m, float* v, int64_t lo,
-                            int64_t n, int32_t world, int32_t rank, const int64_t* step, NcfAdamHyper h,
-                            void* stream) {
+                            int64_t n, int32_t world, int32_t rank, float grad_scale, const int64_t* step,
+                            NcfAdamHyper h, void* stream) {
   NCF_REQUIRE(grad_bufs && param_bufs && m && v && step, "ncf_adam_p2p: null pointer");
   NCF_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "ncf_adam_p2p: world must be 1..8 (one node)");
   NCF_REQUIRE(lo >= 0 && n >= 0 && (lo & 3) == 0 && (n & 3) == 0, "ncf_adam_p2p: lo and n must be multiples of 4");
@@ -746,7 +752,7 @@ extern "C" int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_buf
   if (n == 0) return NCF_OK;
   adam_p2p_kernel<<<ncf::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(
       b, b.p[rank], reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), lo / 4, n / 4, world,
-      1.f / (float)world, step, make_const(h));
+      grad_scale, step, make_const(h));
   NCF_LAUNCH_CHECK("adam_p2p_kernel");
   return NCF_OK;
 }

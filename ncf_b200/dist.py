@@ -79,7 +79,9 @@ def average_(t: torch.Tensor, world: int):
 class ReplicatedDataParallel:
     """Data-parallel wrapper of a FusedTrainStep (see the module docstring for the two layouts)."""
 
-    def __init__(self, ts, check_replicas: bool = True, partition_users=None):
+    def __init__(self, ts, check_replicas: bool = True, partition_users=None, global_batch=None):
+        """`global_batch`: samples per step over all ranks (default ts.max_batch * world); decides at
+        construction whether steps run the all-rows optimiser, which the peer-memory tail requires."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.ts = ts
@@ -109,8 +111,17 @@ class ReplicatedDataParallel:
         first_item = g.g_item_gmf if g.g_item_gmf is not None else g.g_item_mlp
         self.n_user_flat = ((first_item if first_item is not None else g.g_tower).data_ptr() - g.flat.data_ptr()) // 4
         self.n_rows_flat = (g.g_tower.data_ptr() - g.flat.data_ptr()) // 4
-        self.comm_stream, self.sharded = None, None
+        self.comm_stream, self.sharded, self.tail = None, None, None
         if self.partition_users:
+            # The replicated tail [item GMF | item MLP | tower] over peer memory (default on one NVLink node
+            # when steps run the all-rows optimiser; NCF_DP_P2P_TAIL=0 keeps the NCCL all-reduce): one kernel
+            # does reduce -> Adam -> broadcast of that tail (ncf_adam_p2p) instead of all-reduce + Adam.
+            want = os.environ.get("NCF_DP_P2P_TAIL", "1") != "0"
+            if want and dev.type == "cuda" and dist.get_backend() == "nccl" and 2 <= self.world <= 8 \
+                    and ts.dense_adam(int(global_batch) if global_batch else ts.max_batch * self.world) \
+                    and os.environ.get("NCF_ADAM_DENSE") != "0" \
+                    and g.g_item_gmf is not None and g.g_item_mlp is not None and ts.model.factor_num % 4 == 0:
+                self._setup_p2p_tail()
             # opt-in (NCF_DP_OVERLAP=1): the item-row gradients are complete when the tower kernel is (before the
             # weight-gradient kernel on the tcgen05 path), so their all-reduce can run on a side stream under that
             # kernel.  Measured at N=2 on B200: the NCCL CTAs take SMs from the one-CTA-per-SM weight-gradient
@@ -138,6 +149,58 @@ class ReplicatedDataParallel:
             auto = True   # the peer-memory exchange exists in the sharded step only
         if dev.type == "cuda" and (want_shard == "1" or (want_shard is None and auto)):
             self._setup_sharded()
+
+    # -- the replicated tail over peer memory -------------------------------------------------------------------------
+    def _setup_p2p_tail(self):
+        """Re-homes the gradients and parameters of the item tables and the tower into two buffers the other
+        ranks map through CUDA IPC, laid out [item GMF | item MLP | tower] and padded so that they split evenly:
+        rank r owns elements [r * per, (r + 1) * per) and keeps the Adam moments of that slice only."""
+        ts, W, dev = self.ts, self.world, self.ts.device
+        ts.flush()
+        model, g, st = ts.model, ts.grads, ts.state
+        tower_params = [q for lin in model.linears() for q in (lin.weight, lin.bias)]
+        tower_params += [model.predict_layer.weight, model.predict_layer.bias]
+        n_ig, n_im, nt = g.g_item_gmf.numel(), g.g_item_mlp.numel(), g.g_tower.numel()
+        pad4 = lambda n: (n + 3) // 4 * 4
+        o_im, o_t = pad4(n_ig), pad4(n_ig) + pad4(n_im)
+        n = o_t + pad4(nt)
+        per = -(-n // (4 * W)) * 4
+        n_pad = per * W
+        gbuf, pbuf = ops.PeerBuffer(n_pad, dev), ops.PeerBuffer(n_pad, dev)
+        gt, pt = gbuf.tensor, pbuf.tensor
+        mflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        vflat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        for off, cnt, gname, param, mname, vname in ((0, n_ig, "g_item_gmf", model.embed_item_GMF.weight, "m_item_gmf", "v_item_gmf"),
+                                                      (o_im, n_im, "g_item_mlp", model.embed_item_MLP.weight, "m_item_mlp", "v_item_mlp")):
+            old = getattr(g, gname)
+            gt[off:off + cnt].copy_(old.reshape(-1))
+            pt[off:off + cnt].copy_(param.data.reshape(-1))
+            mflat[off:off + cnt].copy_(getattr(st, mname).reshape(-1))
+            vflat[off:off + cnt].copy_(getattr(st, vname).reshape(-1))
+            setattr(g, gname, gt[off:off + cnt].view_as(old))
+            param.data = pt[off:off + cnt].view_as(param.data)
+        gt[o_t:o_t + nt].copy_(g.g_tower)
+        mflat[o_t:o_t + nt].copy_(st.m_tower)
+        vflat[o_t:o_t + nt].copy_(st.v_tower)
+        g.g_tower = gt[o_t:o_t + nt]
+        o = o_t
+        for q in tower_params:              # the flat tower order of the C ABI (ncf_tower_param_count)
+            cnt = q.numel()
+            pt[o:o + cnt].copy_(q.data.reshape(-1))
+            q.data = pt[o:o + cnt].view_as(q.data)
+            o += cnt
+        assert o == o_t + nt, "tower layout mismatch"
+        g.flat = None                        # the gradients are no longer one allocation
+        lo = self.rank * per
+        handles = [None] * W
+        dist.all_gather_object(handles, (gbuf.handle(), pbuf.handle()))
+        self.tail = {"per": per, "lo": lo, "g": gt, "p": pt, "bufs": (gbuf, pbuf),
+                     "m": mflat[lo:lo + per].clone(), "v": vflat[lo:lo + per].clone(),
+                     "flag": torch.zeros(1, dtype=torch.float32, device=dev),
+                     "gptrs": [gbuf.address if r == self.rank else gbuf.open_peer(handles[r][0]) for r in range(W)],
+                     "pptrs": [pbuf.address if r == self.rank else pbuf.open_peer(handles[r][1]) for r in range(W)]}
+        ts._refresh()
+        dist.barrier()                       # nobody steps before every rank has mapped every buffer
 
     def _teacher_logits(self, user, item):
         """Teacher forward for response KD (reference src/distillation/response.py:15-19), or None."""
@@ -178,6 +241,25 @@ class ReplicatedDataParallel:
             t_logits, alpha = self._teacher_logits(user, item)
             ops.train_step_grads_norm(ts._m, ts._g, user, item, label, B, ts.loss_accum, ts.workspace,
                                       teacher_logits=t_logits, alpha=alpha)
+        if self.tail is not None:
+            # reduce -> Adam -> broadcast of the replicated tail in ONE kernel over peer memory: the rank reads its
+            # slice of every rank's gradients (NVLink loads), sums them (every rank divided by the global batch
+            # already), steps its slice and stores the new parameters into every rank's buffer.  The two
+            # one-element all-reduces are the rank barriers around it (stream-ordered on every rank).
+            if not dense:
+                raise ops._lib.NcfError("the peer-memory tail runs with the all-rows optimiser only "
+                                        "(set NCF_DP_P2P_TAIL=0 for batches that touch few rows)")
+            tl = self.tail
+            dist.all_reduce(tl["flag"])          # every rank's gradients are complete
+            ops.adam_p2p(tl["gptrs"], tl["pptrs"], tl["m"], tl["v"], tl["lo"], self.rank, ts.state.step, ts.lr,
+                         ts.betas[0], ts.betas[1], ts.eps, grad_scale=1.0)
+            dist.all_reduce(tl["flag"])          # every rank has read these gradients and written its parameters
+            tl["g"].zero_()
+            ops.adam_step_dense_range(ts._m, ts._g, ts._s, self.user_lo, self.user_hi, ts.lr, ts.betas[0],
+                                      ts.betas[1], ts.eps, parts=ops.PART_USERS)
+            ts._dirty = False
+            ts.num_steps += 1
+            return
         # every rank holds (sum over its samples) / B: the global-mean gradient is the plain sum
         flat = ts.grads.flat
         if self.comm_stream is not None and b > 0:

@@ -420,12 +420,16 @@ def adam_step_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState, lr, beta1=0.9, be
           "ncf_adam_step_dense")
 
 
+PART_USERS, PART_ITEMS, PART_TOWER = 1, 2, 4
+
+
 def adam_step_dense_range(m: NcfModel, g: NcfGrads, s: NcfAdamState, user_lo: int, user_hi: int, lr,
-                          beta1=0.9, beta2=0.999, eps=1e-8):
-    """The all-rows Adam step over user rows [user_lo, user_hi) and every item row."""
+                          beta1=0.9, beta2=0.999, eps=1e-8, parts: int = 7):
+    """The all-rows Adam step over user rows [user_lo, user_hi) and every item row; `parts` masks what this
+    call updates (PART_USERS | PART_ITEMS | PART_TOWER)."""
     check(_lib.load().ncf_adam_step_dense_range(C.byref(m), C.byref(g), C.byref(s),
                                                 NcfAdamHyper(lr, beta1, beta2, eps), int(user_lo), int(user_hi),
-                                                current_stream()), "ncf_adam_step_dense_range")
+                                                int(parts), current_stream()), "ncf_adam_step_dense_range")
 
 
 def adam_range(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, step: torch.Tensor,
@@ -436,13 +440,14 @@ def adam_range(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tenso
 
 
 def adam_p2p(grad_ptrs, param_ptrs, m: torch.Tensor, v: torch.Tensor, lo: int, rank: int, step: torch.Tensor,
-             lr, beta1=0.9, beta2=0.999, eps=1e-8):
+             lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=None):
     """Sharded Adam step with the gradient exchange inside the kernel (ncf_adam_p2p): `grad_ptrs` /
     `param_ptrs` are the device addresses of every rank's flat gradient / parameter buffer."""
     world = len(grad_ptrs)
     ga = (C.c_void_p * world)(*grad_ptrs)
     pa = (C.c_void_p * world)(*param_ptrs)
-    check(_lib.load().ncf_adam_p2p(ga, pa, ptr(m), ptr(v), lo, m.numel(), world, rank, ptr(step),
+    scale = 1.0 / world if grad_scale is None else float(grad_scale)
+    check(_lib.load().ncf_adam_p2p(ga, pa, ptr(m), ptr(v), lo, m.numel(), world, rank, scale, ptr(step),
                                    NcfAdamHyper(lr, beta1, beta2, eps), current_stream()), "ncf_adam_p2p")
 
 

@@ -39,7 +39,7 @@ def main():
     torch.manual_seed(0)
     model = NCF(U, I, f, L, 0.0, "NeuMF-end").to(dev)
     ts = FusedTrainStep(model, "adam", 1e-3, max_batch=B, teacher=teacher, alpha=0.5)
-    dp = ReplicatedDataParallel(ts)
+    dp = ReplicatedDataParallel(ts, global_batch=B)
     lo, hi = partition(B, world, rank)
     for t in range(T):
         if dp.partition_users:   # the samples of the global batch whose user this rank owns
@@ -73,7 +73,8 @@ def main():
         total += d.numel()
     if rank == 0:
         print(json.dumps({"divergence": divergence, "vs_single_process": worst, "share_over": over / total, "world": world,
-                          "partitioned": dp.partition_users, "loss_dp": loss_dp, "loss_single": loss_ref}))
+                          "partitioned": dp.partition_users, "p2p_tail": dp.tail is not None, "loss_dp": loss_dp,
+                          "loss_single": loss_ref}))
     dist.destroy_process_group()
 
 

@@ -68,9 +68,9 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.ncf_ipc_open(None, ctypes.byref(out)) == -1
     ptrs = (ctypes.c_void_p * 9)(*([16] * 9))
     hyper = _lib.NcfAdamHyper(1e-3, 0.9, 0.999, 1e-8)
-    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 0, 4, 9, 0, 16, hyper, None) == -1
+    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 0, 4, 9, 0, 1.0, 16, hyper, None) == -1
     assert b"world" in lib.ncf_last_error()
-    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 2, 4, 2, 0, 16, hyper, None) == -1   # lo not a multiple of 4
+    assert lib.ncf_adam_p2p(ptrs, ptrs, 16, 16, 2, 4, 2, 0, 1.0, 16, hyper, None) == -1   # lo not a multiple of 4
 
 
 def test_no_cpu_fallback():
