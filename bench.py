@@ -500,6 +500,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # batch buffers is captured once (at N>1 with its NCCL all-reduce) and replayed: two launches per
     # step from the host (shuffle + graph) - the same windows-of-graphs scheme train_epoch uses
     use_step_graph = not args.no_graph and (dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0"))
+    use_e2e_graph = use_step_graph
+    if dp is not None and os.environ.get("NCF_BENCH_STEP_GRAPH", "0") != "1":
+        use_step_graph = False      # device-resident loop at N>1: eager launches (see the note at the timed loop)
     for k in range(W):
         one_step(k)
         if k == 1 and use_step_graph:
@@ -671,7 +674,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # the current step computes; every step still copies its own inputs from pinned host memory and reads
     # its loss back.
     hf = None
-    if use_step_graph:
+    if use_e2e_graph:
         from ncf_b200.trainer import HostFedTrainer
         for k in range(2):  # every kernel loaded before capture
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])

@@ -22,17 +22,19 @@ def _run_dp(port, **env):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("variant", ["lazy", "teacher", "big", "big_nccl"])
+@pytest.mark.parametrize("variant", ["lazy", "teacher", "tail_small", "big", "big_nccl"])
 def test_user_partitioned_dp_two_gpus(variant):
     """Default layout: every rank owns a user range and trains on its users' samples; only the item-table
     and tower gradients are exchanged.  `big` runs the tcgen05 path with the all-rows optimiser and the
     replicated tail over peer memory (reduce + Adam + broadcast in one kernel, ncf_adam_p2p); `big_nccl` the
     same with the NCCL all-reduce."""
     env = {"lazy": {}, "teacher": {"DP_TEACHER": "1"}, "big": {"DP_BIG": "1"},
+           "tail_small": {"NCF_ADAM_DENSE": "1", "DP_TEACHER": "1"},   # all-rows optimiser forced: peer-memory tail at a batch
+                                                                      # the mma.sync path runs deterministically (strict bound)
            "big_nccl": {"DP_BIG": "1", "NCF_DP_P2P_TAIL": "0"}}[variant]
     res = _run_dp(29515, NCF_DP_PARTITION="1", **env)
     assert res["partitioned"] is True
-    assert res["p2p_tail"] is (variant == "big")
+    assert res["p2p_tail"] is (variant in ("big", "tail_small"))
     assert res["divergence"] == 0.0          # items + tower identical everywhere, user rows from their owners
     if variant.startswith("big"):
         # tcgen05 path: run-dependent accumulation order may flip a ReLU that sits within fp32 rounding of
