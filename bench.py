@@ -501,8 +501,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # step from the host (shuffle + graph) - the same windows-of-graphs scheme train_epoch uses
     use_step_graph = not args.no_graph and (dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0"))
     use_e2e_graph = use_step_graph
-    if dp is not None and os.environ.get("NCF_BENCH_STEP_GRAPH", "0") != "1":
-        use_step_graph = False      # device-resident loop at N>1: eager launches (see the note at the timed loop)
+    if dp is not None and os.environ.get("NCF_BENCH_STEP_GRAPH", "1") == "0":
+        use_step_graph = False      # experiment knob: eager launches in the device-resident loop at N>1
     for k in range(W):
         one_step(k)
         if k == 1 and use_step_graph:
@@ -513,7 +513,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # At N>1 the loop waits for the device every 4th step, as a loop that reads its loss every few steps does: with
-    # all eight ranks running ahead unsynchronised the NCCL steps were measured 8 % slower (0.543 vs 0.497 ms at N=8)
+    # all eight ranks running ahead unsynchronised the steps were measured 8 % slower (0.543 vs 0.497 ms at N=8; at
+    # N=2 graph replays cost the same either way: 0.394 vs 0.400 ms - profiles/r02/dp_loop_modes.md)
     sync_every = int(os.environ.get("NCF_BENCH_SYNC_EVERY", "4" if world > 1 else "0"))
     e0.record()
     for k in range(W, W + K):
