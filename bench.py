@@ -631,9 +631,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(10):
-            dist.all_reduce(tl["flag"])
+            tl["barrier"]()
             ops.adam_p2p(tl["gptrs"], tl["pptrs"], tl["m"], tl["v"], tl["lo"], rank, ts.state.step, 0.0, grad_scale=1.0)
-            dist.all_reduce(tl["flag"])
+            tl["barrier"]()
         c1.record()
         barrier()
         tl["m"].copy_(m0); tl["v"].copy_(v0)           # lr = 0 left the parameters alone; restore the moments
@@ -641,7 +641,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         per_bytes = tl["per"] * 4
         wire = (world - 1) * per_bytes                  # gradient slices read from the peers = parameter slices written to them
         nvlink = {"exchange": "ncf_adam_p2p: reduce + Adam + broadcast of [item GMF | item MLP | tower] over peer memory, "
-                              "two one-element all-reduces as rank barriers",
+                              "between two rank barriers (ncf_peer_barrier)",
                   "buffer_bytes": tl["g"].numel() * 4, "ms": ex_ms, "bytes_in_per_gpu": wire, "bytes_out_per_gpu": wire,
                   "achieved_gbs": wire / (ex_ms * 1e-3) / 1e9, "peak_gbs_per_direction": NVLINK_GBS,
                   "frac": wire / (ex_ms * 1e-3) / 1e9 / NVLINK_GBS, "share_of_step": ex_ms / (ms_total / K)}

@@ -318,6 +318,13 @@ int ncf_adam_finish_dense(const NcfModel* m_host, const NcfGrads* g_host, const 
  * complete before, all ranks done after (then zero the local gradient buffer). */
 int ncf_adam_p2p(const void* const* grad_bufs, void* const* param_bufs, float* m, float* v, int64_t lo, int64_t n,
                  int32_t world, int32_t rank, float grad_scale, const int64_t* step, NcfAdamHyper h, void* stream);
+/* Rank barrier over peer memory for the exchanges above (instead of a one-element NCCL all-reduce): flag_peers
+ * is a HOST array of `world` device pointers to every rank's flag array (uint32[world], zero-initialised,
+ * ncf_peer_alloc + ncf_ipc_open); epoch_counter is a local device uint32 (zero-initialised) that counts this
+ * rank's barriers, so the call can be captured in a CUDA graph.  Every rank must issue the same sequence of
+ * barriers on its stream.  Release / acquire at system scope: writes of earlier kernels on the stream are
+ * visible to what the peers launch after their barrier.  The wait is bounded (trap, not hang). */
+int ncf_peer_barrier(void* const* flag_peers, int32_t world, int32_t rank, uint32_t* epoch_counter, void* stream);
 /* Buffers shared between ranks have to be allocations of their own (CUDA IPC exports whole
  * allocations): ncf_peer_alloc returns zero-filled device memory of the current device, the only
  * memory this library ever owns; ncf_ipc_export writes its 64-byte handle, which the peers turn into

@@ -98,6 +98,7 @@ SIGNATURES = {
     "ncf_adam_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, NcfAdamHyper, _vp]),
     "ncf_adam_finish_dense": (C.c_int, [_P(NcfModel), _P(NcfGrads), _P(NcfAdamState), _vp]),
     "ncf_adam_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _fl, _vp, NcfAdamHyper, _vp]),
+    "ncf_peer_barrier": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "ncf_peer_alloc": (C.c_int, [_i64, _vp]),
     "ncf_peer_free": (C.c_int, [_vp]),
     "ncf_ipc_export": (C.c_int, [_vp, _vp]),

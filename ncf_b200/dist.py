@@ -66,6 +66,15 @@ def gather_indices(user: torch.Tensor, item: torch.Tensor, world: int):
     return gu, gi
 
 
+def make_rank_barrier(dev):
+    """A stream-ordered rank barrier as a callable: the peer-memory barrier kernel (default on one node), or a
+    one-element NCCL all-reduce (NCF_PEER_BARRIER=0)."""
+    if os.environ.get("NCF_PEER_BARRIER", "1") != "0" and dist.get_world_size() <= 8 and dev.type == "cuda":
+        return ops.PeerBarrier(dev).wait
+    flag = torch.zeros(1, dtype=torch.float32, device=dev)
+    return lambda: dist.all_reduce(flag)
+
+
 def average_(t: torch.Tensor, world: int):
     """In-place rank average (NCCL has ReduceOp.AVG; gloo does not)."""
     if dist.get_backend() == "nccl":
@@ -196,11 +205,14 @@ class ReplicatedDataParallel:
         dist.all_gather_object(handles, (gbuf.handle(), pbuf.handle()))
         self.tail = {"per": per, "lo": lo, "g": gt, "p": pt, "bufs": (gbuf, pbuf),
                      "m": mflat[lo:lo + per].clone(), "v": vflat[lo:lo + per].clone(),
-                     "flag": torch.zeros(1, dtype=torch.float32, device=dev),
+                     "barrier": self._make_barrier(dev),
                      "gptrs": [gbuf.address if r == self.rank else gbuf.open_peer(handles[r][0]) for r in range(W)],
                      "pptrs": [pbuf.address if r == self.rank else pbuf.open_peer(handles[r][1]) for r in range(W)]}
         ts._refresh()
         dist.barrier()                       # nobody steps before every rank has mapped every buffer
+
+    def _make_barrier(self, dev):
+        return make_rank_barrier(dev)
 
     def _teacher_logits(self, user, item):
         """Teacher forward for response KD (reference src/distillation/response.py:15-19), or None."""
@@ -250,10 +262,10 @@ class ReplicatedDataParallel:
                 raise ops._lib.NcfError("the peer-memory tail runs with the all-rows optimiser only "
                                         "(set NCF_DP_P2P_TAIL=0 for batches that touch few rows)")
             tl = self.tail
-            dist.all_reduce(tl["flag"])          # every rank's gradients are complete
+            tl["barrier"]()                      # every rank's gradients are complete
             ops.adam_p2p(tl["gptrs"], tl["pptrs"], tl["m"], tl["v"], tl["lo"], self.rank, ts.state.step, ts.lr,
                          ts.betas[0], ts.betas[1], ts.eps, grad_scale=1.0)
-            dist.all_reduce(tl["flag"])          # every rank has read these gradients and written its parameters
+            tl["barrier"]()                      # every rank has read these gradients and written its parameters
             tl["g"].zero_()
             ops.adam_step_dense_range(ts._m, ts._g, ts._s, self.user_lo, self.user_hi, ts.lr, ts.betas[0],
                                       ts.betas[1], ts.eps, parts=ops.PART_USERS)
@@ -553,11 +565,8 @@ class RowShardedTrainer:
         self._rows_gmf = self._bufs["rows_gmf"].tensor.view(cap, self.f)
         self._rows_mlp = self._bufs["rows_mlp"].tensor.view(cap, self.d)
         self._cursor = torch.zeros(max(W, 4), dtype=torch.int32, device=dev)
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._barrier = make_rank_barrier(dev)   # stream-ordered: every rank's preceding kernels are complete
         dist.barrier()                    # nobody steps before every rank has mapped every buffer
-
-    def _barrier(self):
-        dist.all_reduce(self._flag)       # stream-ordered: every rank's preceding kernels are complete
 
     def _step_p2p(self, user, item, label, B_global):
         ts, W, m = self.ts, self.world, self.model

@@ -495,6 +495,26 @@ class PeerBuffer:
             self.address = None
 
 
+class PeerBarrier:
+    """Rank barrier over peer memory (ncf_peer_barrier): a flag array per rank, mapped by every other rank.
+    Collective construction (torch.distributed must be initialised); `wait()` enqueues the barrier on the
+    current stream and can be captured in a CUDA graph."""
+
+    def __init__(self, device: torch.device):
+        import torch.distributed as dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.flags = PeerBuffer(8, device, torch.int32)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.flags.handle())
+        self.ptrs = [self.flags.address if r == self.rank else self.flags.open_peer(handles[r]) for r in range(self.world)]
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier()
+
+    def wait(self) -> None:
+        check(_lib.load().ncf_peer_barrier(_ptr_array(self.ptrs), self.world, self.rank, ptr(self.epoch), current_stream()),
+              "ncf_peer_barrier")
+
+
 def adam_finish_dense(m: NcfModel, g: NcfGrads, s: NcfAdamState):
     check(_lib.load().ncf_adam_finish_dense(C.byref(m), C.byref(g), C.byref(s), current_stream()),
           "ncf_adam_finish_dense")
