@@ -105,13 +105,16 @@ __global__ void __launch_bounds__(256) csr_sort_rows_warp_kernel(const int64_t* 
   }
 }
 
+// rows with lo < n <= hi items; launched once per size class so that the many medium rows run on CTAs with a
+// small shared-memory footprint (several per SM) and only the few very long ones take a 128 KB CTA
 __global__ void __launch_bounds__(256) csr_sort_rows_cta_kernel(const int64_t* __restrict__ rowptr, int64_t U,
-                                                                const int32_t* __restrict__ tmp, int32_t* __restrict__ col) {
+                                                                const int32_t* __restrict__ tmp, int32_t* __restrict__ col,
+                                                                int lo, int hi) {
   extern __shared__ int32_t big[];
   for (int64_t u = blockIdx.x; u < U; u += gridDim.x) {
     const int64_t b = rowptr[u];
     const int64_t n = rowptr[u + 1] - b;
-    if (n <= kWarpRow || n > kCtaRow) continue;   // uniform over the CTA
+    if (n <= lo || n > hi) continue;   // uniform over the CTA
     int N = 1;
     while (N < n) N <<= 1;
     for (int i = threadIdx.x; i < N; i += blockDim.x) big[i] = i < n ? tmp[b + i] : 0x7fffffff;
@@ -270,8 +273,11 @@ extern "C" int ncf_csr_build(const int64_t* pos_user, const int64_t* pos_item, i
       NCF_CUDA(cudaFuncSetAttribute(csr_sort_rows_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaRow * 4));
       attr_set = true;
     }
-    csr_sort_rows_cta_kernel<<<ncf::num_sms(), T, kCtaRow * 4, st>>>(rowptr, user_num, tmp, col);
-    NCF_LAUNCH_CHECK("csr_sort_rows_cta");
+    constexpr int kMidRow = 4096;   // 16 KB of shared memory: 8+ CTAs per SM
+    csr_sort_rows_cta_kernel<<<ncf::num_sms() * 8, T, kMidRow * 4, st>>>(rowptr, user_num, tmp, col, kWarpRow, kMidRow);
+    NCF_LAUNCH_CHECK("csr_sort_rows_cta(mid)");
+    csr_sort_rows_cta_kernel<<<ncf::num_sms(), T, kCtaRow * 4, st>>>(rowptr, user_num, tmp, col, kMidRow, kCtaRow);
+    NCF_LAUNCH_CHECK("csr_sort_rows_cta(long)");
     csr_rank_kernel<<<grid_for(P, T), T, 0, st>>>(pos_user, pos_item, P, user_num, rowptr, tmp, col);
     NCF_LAUNCH_CHECK("csr_rank");
   }
