@@ -464,6 +464,20 @@ __global__ void finalize_step_kernel(int64_t* step, int32_t* tcount) {
   tcount[1] = 0;
 }
 
+// Upper bound on the rows registered since the last optimiser step (set by the mark / prepare entries, which
+// know the batch size).  Only a launch-size hint: the row kernels walk the touched lists with grid-stride
+// loops, so any grid is correct - but 1184 CTAs for the 512 rows of a batch of 256 cost 11 us of launch and
+// drain where 64 CTAs cost 4.
+thread_local int64_t g_rows_hint = 0;
+
+int rows_grid(int64_t rows) {
+  const int64_t cap = (int64_t)ncf::num_sms() * 8;
+  if (rows <= 0) return (int)cap;
+  int64_t blocks = (rows + kWarps - 1) / kWarps;   // one warp per row
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
 AdamConst make_const(NcfAdamHyper h) {
   AdamConst c;
   c.lr = h.lr; c.b1 = h.beta1; c.b2 = h.beta2; c.eps = h.eps;
@@ -598,9 +612,10 @@ static int adam_step_impl(const NcfModel* m, const NcfGrads* g, const NcfAdamSta
     adam_rows_kernel<3><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
     NCF_LAUNCH_CHECK("adam_rows_kernel");
   } else {
-    adam_rows_kernel<0><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+    adam_rows_kernel<0><<<rows_grid(g_rows_hint), kThreads, 0, st>>>(q);
     NCF_LAUNCH_CHECK("adam_rows_kernel");
   }
+  g_rows_hint = 0;
   if (parts & kPartTower) {
     DenseParams dq{};
     fill_dense(dq, m);
@@ -621,6 +636,7 @@ static int launch_mark(const NcfModel* m, const NcfGrads* g, const int64_t* user
                                                g->user_flag, g->item_flag, g->user_list,
                                                g->item_list, g->touched_count);
   NCF_LAUNCH_CHECK("mark_rows_kernel");
+  g_rows_hint += 2 * B;
   return NCF_OK;
 }
 
@@ -648,6 +664,7 @@ extern "C" int ncf_mark_rows_side(const NcfModel* m, const NcfGrads* g, const in
       rows, n, side ? m->item_num : m->user_num, side ? g->item_flag : g->user_flag,
       side ? g->item_list : g->user_list, g->touched_count + side);
   NCF_LAUNCH_CHECK("mark_side_kernel");
+  g_rows_hint += n;
   return NCF_OK;
 }
 
@@ -660,7 +677,7 @@ extern "C" int ncf_adam_catchup(const NcfModel* m, const NcfGrads* g, const NcfA
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);
-  adam_rows_kernel<2><<<ncf::num_sms() * 8, kThreads, 0, (cudaStream_t)stream>>>(q);
+  adam_rows_kernel<2><<<rows_grid(g_rows_hint), kThreads, 0, (cudaStream_t)stream>>>(q);
   NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
   return NCF_OK;
 }
@@ -678,7 +695,7 @@ extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfA
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);
-  adam_rows_kernel<2><<<ncf::num_sms() * 8, kThreads, 0, st>>>(q);
+  adam_rows_kernel<2><<<rows_grid(g_rows_hint), kThreads, 0, st>>>(q);
   NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
   return NCF_OK;
 }
@@ -703,7 +720,8 @@ extern "C" int ncf_sgd_step(const NcfModel* m, const NcfGrads* g, float lr, void
   cudaStream_t st = (cudaStream_t)stream;
   RowsParams q{};
   fill_rows(q, m, g, nullptr);
-  sgd_rows_kernel<<<ncf::num_sms() * 8, kThreads, 0, st>>>(q, lr);
+  sgd_rows_kernel<<<rows_grid(g_rows_hint), kThreads, 0, st>>>(q, lr);
+  g_rows_hint = 0;
   NCF_LAUNCH_CHECK("sgd_rows_kernel");
   DenseParams dq{};
   fill_dense(dq, m);
