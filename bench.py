@@ -83,12 +83,15 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.001):
+        self.period = float(os.environ.get("NCF_BENCH_CLOCK_PERIOD", period))
         self.gpu, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
         self._stop, self._thread, self._nvml = None, None, None
 
     def start(self):
         import threading
+        if os.environ.get("NCF_BENCH_NO_CLOCKS") == "1":     # experiment knob: no NVML polling at all
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -111,7 +114,7 @@ class ClockSampler:
                     self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     pass
-                self._stop.wait(0.001)
+                self._stop.wait(self.period)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
