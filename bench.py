@@ -76,17 +76,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML (a thread, every 1 ms; an NVML query itself takes
-    a few ms) from the start of the device-resident timed region to the end of the end-to-end one (the GPU
-    is under load throughout: timed steps, per-phase passes, host-fed steps) — the same fields as the
-    nvidia-smi clocks line of B200_PROFILING.md."""
+    """SM clocks and throttle reasons sampled through NVML by ONE thread of rank 0 for every GPU of the job
+    (every `period` seconds, 5 ms by default), from the start of the device-resident timed region to the end
+    of the end-to-end one — the same fields as the nvidia-smi clocks line of B200_PROFILING.md.
+    Only rank 0 polls: with a polling thread in each of 8 ranks the timed loop itself ran 20 % slower
+    (0.452 vs 0.375 ms/step at N=8, whatever the period: NVML queries from many processes serialise in the
+    driver and hold up launches; one poller does not, as at N=1)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index, period=0.001):
+    def __init__(self, n_gpus, period=0.005):
         self.period = float(os.environ.get("NCF_BENCH_CLOCK_PERIOD", period))
-        self.gpu, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
-        self._stop, self._thread, self._nvml = None, None, None
+        self.n = n_gpus
+        self.samples = [[] for _ in range(n_gpus)]
+        self.mask = [0] * n_gpus
+        self.max_mhz = None
+        self._stop, self._thread = None, None
 
     def start(self):
         import threading
@@ -95,25 +100,25 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES when it lists indices
+            # honour CUDA_VISIBLE_DEVICES when it lists indices (local rank r runs on the r-th visible GPU)
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = self.gpu
+            idx = list(range(self.n))
             if vis and all(x.strip().isdigit() for x in vis.split(",")):
-                idx = int(vis.split(",")[self.gpu])
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            self._nvml = pynvml
+                idx = [int(x) for x in vis.split(",")][:self.n]
+            handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in idx]
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handles[0], pynvml.NVML_CLOCK_SM))
         except Exception:
             return
         self._stop = threading.Event()
 
         def loop():
             while not self._stop.is_set():
-                try:
-                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    pass
+                for g, h in enumerate(handles):
+                    try:
+                        self.samples[g].append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask[g] |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
                 self._stop.wait(self.period)
 
         self._thread = threading.Thread(target=loop, daemon=True)
@@ -123,12 +128,13 @@ class ClockSampler:
         if self._thread is not None:
             self._stop.set()
             self._thread.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit),
-                "samples": len(s)}
+        med = [sorted(s)[len(s) // 2] if s else None for s in self.samples]
+        reasons = sorted({n for m in self.mask for bit, n in self.REASONS.items() if m & bit})
+        out = {"sm_mhz": med[0], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples[0])}
+        if self.n > 1:
+            have = [m for m in med if m is not None]
+            out["all_gpus"] = {"sm_mhz_per_gpu": med, "sm_mhz_min_of_medians": min(have) if have else None}
+        return out
 
 
 # ---- the reference's own implementation of the path (CPU arm, GPU-eager bar) --------------------------
@@ -511,9 +517,10 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         if k == 1 and use_step_graph:
             barrier()
             graphs = [ts.capture(*bufs[j], B, step_fn if dp is not None else None) for j in range(2)]
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(world) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # At N>1 the loop waits for the device every 4th step, as a loop that reads its loss every few steps does: with
     # all eight ranks running ahead unsynchronised the steps were measured 8 % slower (0.543 vs 0.497 ms at N=8; at
@@ -712,14 +719,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     for k in range(W, W + K):
         e2e_step(k)
     barrier()
-    clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
-    if world > 1:               # every rank watched its own GPU: keep the slowest one in view as well
-        allc = [None] * world
-        dist.all_gather_object(allc, clocks)
-        mhz = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
-        clocks["all_ranks"] = {"sm_mhz_min_of_medians": min(mhz) if mhz else None,
-                               "sm_mhz_per_rank": [c["sm_mhz"] for c in allc],
-                               "reasons": sorted({r for c in allc for r in c["reasons"]})}
+    clocks = sampler.stop() if sampler is not None else None   # rank 0 watched every GPU of the job
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
     used_graph = hf is not None
