@@ -76,22 +76,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clocks and throttle reasons sampled through NVML by ONE thread of rank 0 for every GPU of the job
-    (every `period` seconds, 5 ms by default), from the start of the device-resident timed region to the end
-    of the end-to-end one — the same fields as the nvidia-smi clocks line of B200_PROFILING.md.
-    Only rank 0 polls: with a polling thread in each of 8 ranks the timed loop itself ran 20 % slower
-    (0.452 vs 0.375 ms/step at N=8, whatever the period: NVML queries from many processes serialise in the
-    driver and hold up launches; one poller does not, as at N=1)."""
+    """SM clock and throttle reasons sampled through NVML (a thread per rank for its own GPU, every 5 ms)
+    from the start of the device-resident timed region to the end of the end-to-end one (the GPU is under
+    load throughout: timed steps, per-phase passes, host-fed steps) — the same fields as the nvidia-smi
+    clocks line of B200_PROFILING.md.  The polling is not free at N=8: the same loop ran at 0.375 ms/step
+    without it and 0.45 ms/step with it (per-rank pollers at 1 ms or 20 ms alike; one poller on rank 0 for
+    all eight GPUs: 0.56) — NVML queries from the ranks hold up launches that every other rank then waits
+    for at the step's barrier.  `value` is measured WITH the polling; the line also carries the same loop
+    without it (`unsampled_loop`)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, n_gpus, period=0.005):
+    def __init__(self, gpu_index, period=0.005):
         self.period = float(os.environ.get("NCF_BENCH_CLOCK_PERIOD", period))
-        self.n = n_gpus
-        self.samples = [[] for _ in range(n_gpus)]
-        self.mask = [0] * n_gpus
-        self.max_mhz = None
-        self._stop, self._thread = None, None
+        self.gpu, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
+        self._stop, self._thread, self._nvml = None, None, None
 
     def start(self):
         import threading
@@ -100,25 +99,25 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES when it lists indices (local rank r runs on the r-th visible GPU)
+            # honour CUDA_VISIBLE_DEVICES when it lists indices
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = list(range(self.n))
+            idx = self.gpu
             if vis and all(x.strip().isdigit() for x in vis.split(",")):
-                idx = [int(x) for x in vis.split(",")][:self.n]
-            handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in idx]
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handles[0], pynvml.NVML_CLOCK_SM))
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
         except Exception:
             return
         self._stop = threading.Event()
 
         def loop():
             while not self._stop.is_set():
-                for g, h in enumerate(handles):
-                    try:
-                        self.samples[g].append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        self.mask[g] |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                    except Exception:
-                        pass
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
                 self._stop.wait(self.period)
 
         self._thread = threading.Thread(target=loop, daemon=True)
@@ -128,13 +127,12 @@ class ClockSampler:
         if self._thread is not None:
             self._stop.set()
             self._thread.join(timeout=2)
-        med = [sorted(s)[len(s) // 2] if s else None for s in self.samples]
-        reasons = sorted({n for m in self.mask for bit, n in self.REASONS.items() if m & bit})
-        out = {"sm_mhz": med[0], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples[0])}
-        if self.n > 1:
-            have = [m for m in med if m is not None]
-            out["all_gpus"] = {"sm_mhz_per_gpu": med, "sm_mhz_min_of_medians": min(have) if have else None}
-        return out
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit),
+                "samples": len(s)}
 
 
 # ---- the reference's own implementation of the path (CPU arm, GPU-eager bar) --------------------------
@@ -433,6 +431,7 @@ def run_ours(args):
         "sampler": sampler,
         "small_config": small_config_run(dev) if extras else None,
         "gpu_eager_reference": gpu_eager_reference_run(dev, hbm_peak) if extras else None,
+        "unsampled_loop": st["unsampled"],
         "row_sharded": row_sharded,
         "tower_math": args.tower_math,
     }
@@ -517,10 +516,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         if k == 1 and use_step_graph:
             barrier()
             graphs = [ts.capture(*bufs[j], B, step_fn if dp is not None else None) for j in range(2)]
-    sampler = ClockSampler(world) if rank == 0 else None
+    sampler = ClockSampler(local)
     barrier()
-    if sampler is not None:
-        sampler.start()
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # At N>1 the loop waits for the device every 4th step, as a loop that reads its loss every few steps does: with
     # all eight ranks running ahead unsynchronised the steps were measured 8 % slower (0.543 vs 0.497 ms at N=8; at
@@ -719,11 +717,35 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     for k in range(W, W + K):
         e2e_step(k)
     barrier()
-    clocks = sampler.stop() if sampler is not None else None   # rank 0 watched every GPU of the job
+    clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
+    if world > 1:               # every rank watched its own GPU: keep the slowest one in view as well
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        mhz = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
+        clocks["all_ranks"] = {"sm_mhz_min_of_medians": min(mhz) if mhz else None,
+                               "sm_mhz_per_rank": [c["sm_mhz"] for c in allc],
+                               "reasons": sorted({r for c in allc for r in c["reasons"]})}
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * K * B / (e2e_ms * 1e-3)
     used_graph = hf is not None
     del hf
+    # the device-resident loop once more with no NVML polling anywhere in the job (N>1 only; see ClockSampler)
+    unsampled = None
+    if dp is not None:
+        for k in range(2):
+            one_step(k)
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for k in range(W, W + K):
+            one_step(k)
+            if sync_every and (k - W + 1) % sync_every == 0:
+                torch.cuda.current_stream().synchronize()
+        u1.record()
+        barrier()
+        ums = max_over_ranks(u0.elapsed_time(u1))
+        unsampled = {"value": world * K * B / (ums * 1e-3), "ms_per_step": ums / K,
+                     "note": "the timed loop repeated after the clock samplers were stopped"}
 
     # ---- evaluation throughput (second half of the metric: eval users/s): every rank scores its own users ----
     from ncf_b200.metrics import evaluate
@@ -826,6 +848,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     e2e_launch = ("HostFedTrainer: cuda-graph step" + (" (NCCL all-reduce captured)" if dp is not None else "")
                   + ", next batch H2D overlapped") if used_graph else "eager"
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
+                unsampled=unsampled,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,
                 dp_partitioned=(dp.partition_users if dp is not None else True),
                 dp_tail=(dp is not None and dp.tail is not None))
