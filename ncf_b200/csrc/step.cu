@@ -56,6 +56,10 @@ namespace ncf {
 // path needs mma_split_floats(p) floats of workspace for the pre-split weights.
 int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t workspace_bytes,
                      cudaStream_t st) {
+  if (small_eligible(p)) {
+    g_tile_path = 4;
+    return launch_small_forward(p, st);
+  }
   if (umma_eligible(p)) {
     const int64_t need = umma_forward_workspace_floats(p, p.B) * 4;
     if (!workspace || workspace_bytes < need) {
@@ -200,6 +204,12 @@ static int train_common(const NcfModel* m, const NcfGrads* g, const int64_t* use
   p.invB = 1.f / (float)(B_norm > 0 ? B_norm : B);  // mean over the (global) batch
   p.logits = logits_out;
   p.loss_accum = loss_accum;
+  if (ncf::small_eligible(p)) {
+    ncf::g_tile_path = 4;
+    rc = ncf::launch_small_train(p, (cudaStream_t)stream);
+    if (rc != NCF_OK) return rc;
+    return ncf::mark_embedding_grads_done((cudaStream_t)stream);
+  }
   if (ncf::umma_eligible(p)) {
     ncf::g_tile_path = 3;
     return ncf::launch_umma_train(p, ncf::tower_passes(m), (float*)workspace, (cudaStream_t)stream);

@@ -90,6 +90,11 @@ int launch_mma_forward(TileParams& p, int passes, cudaStream_t st);
 int launch_mma_train(TileParams& p, int passes, cudaStream_t st);
 inline int tower_passes(const NcfModel* m) { return m->tower_math == NCF_MATH_TF32 ? 1 : 3; }
 
+// narrow towers, one thread per sample on the FMA pipe (tile_small.cu): factor_num 8, 1..3 layers
+bool small_eligible(const TileParams& p);
+int launch_small_forward(TileParams& p, cudaStream_t st);
+int launch_small_train(TileParams& p, cudaStream_t st);
+
 // tcgen05 path (tile_umma.cu): large batches, tower widths that are power-of-two multiples of 32
 bool umma_eligible(const TileParams& p);  // reads p.B
 int64_t umma_forward_workspace_floats(const TileParams& p, int64_t B);
