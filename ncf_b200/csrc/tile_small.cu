@@ -3,11 +3,13 @@
 //
 // north_star asks for tensor-core MMAs "only for tower layers wide enough to be a real dense contraction":
 // a 64 -> 32 -> 16 -> 8 tower is 2.7 k MACs per sample - one warp of the mma.sync tile kernel spends more
-// time staging fragments than multiplying (37 us for a batch of 256 on 4 CTAs).  Here a warp owns 32 samples:
-// each lane gathers its sample's rows into its own shared-memory row, runs the tower forward and backward
-// over it with the layer weights (and their transposes) resident in shared memory, and the warp then forms
-// the weight gradients of its 32 samples cooperatively (register tiles over the staged activations /
-// deltas) before adding them to the global gradient buffer.  Exact fp32: no operand split, no tolerance
+// time staging fragments than multiplying (37 us for a batch of 256 on 4 CTAs).  Here a CTA of four warps owns
+// a tile of 32 samples: lane = sample, warp = a quarter of every layer's outputs.  The sample's rows are
+// gathered into its own shared-memory row, the tower runs forward and backward over those rows with the layer
+// weights (and their transposes) resident in shared memory, and the CTA then forms the weight gradients of
+// its 32 samples cooperatively (register tiles over the staged activations / deltas) before adding them to
+// the global gradient buffer.  (One warp doing all four quarters measured 29 us for a batch of 256: a single
+// dependent instruction stream per sample.)  Exact fp32: no operand split, no tolerance
 // caveat.  Same contract as the other tile kernels (TileParams; tile_params.cuh).
 //
 // Replaces reference src/ncf/models.py:97-118 (forward), scripts/train_neumf.py:112-114 (criterion + backward)
@@ -47,92 +49,86 @@ struct Ptrs {
   float* h[NCF_MAX_LAYERS + 1];      // activations, row stride W(k) + kPad
 };
 
-// out[n] (n < N, registers) = sum_c in_row[c] * Wt[c][n]   (+ bias, relu by the caller)
-template <int C, int N>
-__device__ __forceinline__ void fwd_layer(const float* __restrict__ in_row, const float* __restrict__ wt,
-                                          const float* __restrict__ bias, float* __restrict__ out_row) {
+constexpr int kWarps = 4;       // warps per tile of 32 samples: lane = sample, warp = a quarter of every layer's work
+constexpr int kThreads = 32 * kWarps;
+
+// out_row[n0 + j] = relu(bias + sum_c in_row[c] * Wt[c][n0 + j]), j < NW: the warp's NW = N / kWarps outputs
+template <int C, int N, int NW>
+__device__ __forceinline__ void fwd_part(const float* __restrict__ in_row, const float* __restrict__ wt,
+                                         const float* __restrict__ bias, float* __restrict__ out_row, int n0) {
+  float acc[NW];
 #pragma unroll
-  for (int n0 = 0; n0 < N; n0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[n0 + j];
+  for (int j = 0; j < NW; ++j) acc[j] = bias[n0 + j];
 #pragma unroll 2
-    for (int c = 0; c < C; c += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(in_row + c);
-      const float xs[4] = {x.x, x.y, x.z, x.w};
+  for (int c = 0; c < C; c += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(in_row + c);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 wa = *reinterpret_cast<const float4*>(wt + (c + q) * N + n0);
-        const float4 wb = *reinterpret_cast<const float4*>(wt + (c + q) * N + n0 + 4);
-        acc[0] = fmaf(xs[q], wa.x, acc[0]); acc[1] = fmaf(xs[q], wa.y, acc[1]);
-        acc[2] = fmaf(xs[q], wa.z, acc[2]); acc[3] = fmaf(xs[q], wa.w, acc[3]);
-        acc[4] = fmaf(xs[q], wb.x, acc[4]); acc[5] = fmaf(xs[q], wb.y, acc[5]);
-        acc[6] = fmaf(xs[q], wb.z, acc[6]); acc[7] = fmaf(xs[q], wb.w, acc[7]);
+    for (int q = 0; q < 4; ++q) {
+      const float* wr = wt + (c + q) * N + n0;
+      if constexpr (NW % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NW; j += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
+          acc[j] = fmaf(xs[q], w4.x, acc[j]); acc[j + 1] = fmaf(xs[q], w4.y, acc[j + 1]);
+          acc[j + 2] = fmaf(xs[q], w4.z, acc[j + 2]); acc[j + 3] = fmaf(xs[q], w4.w, acc[j + 3]);
+        }
+      } else {
+        const float2 w2 = *reinterpret_cast<const float2*>(wr);
+        acc[0] = fmaf(xs[q], w2.x, acc[0]); acc[1] = fmaf(xs[q], w2.y, acc[1]);
       }
     }
-    *reinterpret_cast<float4*>(out_row + n0) = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    *reinterpret_cast<float4*>(out_row + n0 + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
   }
+#pragma unroll
+  for (int j = 0; j < NW; ++j) out_row[n0 + j] = fmaxf(acc[j], 0.f);
 }
 
-// dh[c] = sum_n delta_row[n] * W[n][c]; written back over the input activation row as
-//   MASK: delta_k[c] = dh[c] * (h_k[c] > 0)  into out_row (the delta staging row),   !MASK: dx_0[c] into out_row
-template <int C, int N, bool MASK>
-__device__ __forceinline__ void bwd_layer(const float* __restrict__ delta_row, const float* __restrict__ w,
-                                          const float* __restrict__ h_row, float* __restrict__ out_row) {
+// out_row[c0 + j] = (sum_n delta_row[n] * W[n][c0 + j]) [* (h_row[c0 + j] > 0) if MASK], j < CW = C / kWarps
+template <int C, int N, int CW, bool MASK>
+__device__ __forceinline__ void bwd_part(const float* __restrict__ delta_row, const float* __restrict__ w,
+                                         const float* __restrict__ h_row, float* __restrict__ out_row, int c0) {
+  float acc[CW];
 #pragma unroll
-  for (int c0 = 0; c0 < C; c0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < CW; ++j) acc[j] = 0.f;
 #pragma unroll 2
-    for (int n = 0; n < N; n += 4) {
-      const float4 d4 = *reinterpret_cast<const float4*>(delta_row + n);
-      const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
+  for (int n = 0; n < N; n += 4) {
+    const float4 d4 = *reinterpret_cast<const float4*>(delta_row + n);
+    const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 wa = *reinterpret_cast<const float4*>(w + (n + q) * C + c0);
-        const float4 wb = *reinterpret_cast<const float4*>(w + (n + q) * C + c0 + 4);
-        acc[0] = fmaf(ds[q], wa.x, acc[0]); acc[1] = fmaf(ds[q], wa.y, acc[1]);
-        acc[2] = fmaf(ds[q], wa.z, acc[2]); acc[3] = fmaf(ds[q], wa.w, acc[3]);
-        acc[4] = fmaf(ds[q], wb.x, acc[4]); acc[5] = fmaf(ds[q], wb.y, acc[5]);
-        acc[6] = fmaf(ds[q], wb.z, acc[6]); acc[7] = fmaf(ds[q], wb.w, acc[7]);
+    for (int q = 0; q < 4; ++q) {
+      const float* wr = w + (n + q) * C + c0;
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
+        acc[j] = fmaf(ds[q], w4.x, acc[j]); acc[j + 1] = fmaf(ds[q], w4.y, acc[j + 1]);
+        acc[j + 2] = fmaf(ds[q], w4.z, acc[j + 2]); acc[j + 3] = fmaf(ds[q], w4.w, acc[j + 3]);
       }
     }
-    if (MASK) {
-      const float4 ha = *reinterpret_cast<const float4*>(h_row + c0);
-      const float4 hb = *reinterpret_cast<const float4*>(h_row + c0 + 4);
-      acc[0] = ha.x > 0.f ? acc[0] : 0.f; acc[1] = ha.y > 0.f ? acc[1] : 0.f;
-      acc[2] = ha.z > 0.f ? acc[2] : 0.f; acc[3] = ha.w > 0.f ? acc[3] : 0.f;
-      acc[4] = hb.x > 0.f ? acc[4] : 0.f; acc[5] = hb.y > 0.f ? acc[5] : 0.f;
-      acc[6] = hb.z > 0.f ? acc[6] : 0.f; acc[7] = hb.w > 0.f ? acc[7] : 0.f;
-    }
-    *reinterpret_cast<float4*>(out_row + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(out_row + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
+#pragma unroll
+  for (int j = 0; j < CW; ++j) out_row[c0 + j] = (!MASK || h_row[c0 + j] > 0.f) ? acc[j] : 0.f;
 }
 
-// dW[n][c] += sum_s delta[s][n] * h[s][c] over the warp's 32 samples: lane owns an (N/8) x (C/4) register tile
+// dW[n][c] += sum_s delta[s][n] * h[s][c] over the tile's 32 samples for the warp's columns [cw0, cw0 + C / kWarps):
+// lane owns an (N/8) x (C/16) register tile
 template <int C, int N>
-__device__ __forceinline__ void wgrad_layer(const float* __restrict__ delta_s, const float* __restrict__ h_s,
-                                            float* __restrict__ gw, float* __restrict__ gb, int lane) {
-  constexpr int NB = N / 8, CB = C / 4;
+__device__ __forceinline__ void wgrad_part(const float* __restrict__ delta_s, const float* __restrict__ h_s,
+                                           float* __restrict__ gw, int lane, int cw0) {
+  constexpr int NB = N / 8, CB = C / (4 * kWarps);
   constexpr int SD = N + kPad, SH = C + kPad;
-  const int n0 = (lane >> 2) * NB, c0 = (lane & 3) * CB;
+  const int n0 = (lane >> 2) * NB, c0 = cw0 + (lane & 3) * CB;
   float acc[NB][CB];
 #pragma unroll
   for (int i = 0; i < NB; ++i)
 #pragma unroll
     for (int j = 0; j < CB; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
   for (int s = 0; s < 32; ++s) {
     float dv[NB], hv[CB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) dv[i] = delta_s[s * SD + n0 + i];
 #pragma unroll
-    for (int j = 0; j < CB; j += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(h_s + s * SH + c0 + j);
-      hv[j] = x.x; hv[j + 1] = x.y; hv[j + 2] = x.z; hv[j + 3] = x.w;
-    }
+    for (int j = 0; j < CB; ++j) hv[j] = h_s[s * SH + c0 + j];
 #pragma unroll
     for (int i = 0; i < NB; ++i)
 #pragma unroll
@@ -141,24 +137,17 @@ __device__ __forceinline__ void wgrad_layer(const float* __restrict__ delta_s, c
 #pragma unroll
   for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int j = 0; j < CB; j += 4)
-      red_add4(gw + (n0 + i) * C + c0 + j, make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]));
-  // bias gradient: column sums of delta
-  for (int n = lane; n < N; n += 32) {
-    float sum = 0.f;
-    for (int s = 0; s < 32; ++s) sum += delta_s[s * SD + n];
-    atomicAdd(gb + n, sum);
-  }
+    for (int j = 0; j < CB; ++j) atomicAdd(gw + (n0 + i) * C + c0 + j, acc[i][j]);
 }
 
 template <int L, bool TRAIN>
-__global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) {
+__global__ void __launch_bounds__(kThreads) ncf_small_tile_kernel(const TileParams p) {
   using S = Shape<L>;
   extern __shared__ __align__(16) float smem_small[];
   float* w_sm = smem_small;
   float* h_sm = w_sm + S::weights();
-  float* d_sm = h_sm + S::acts();          // TRAIN: two delta blocks
-  const int lane = threadIdx.x;
+  float* d_sm = h_sm + S::acts();          // TRAIN: two delta blocks, then dl[32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_gmf = p.type != NCF_MLP;
   const int mlp_off = has_gmf ? kF : 0;
 
@@ -170,12 +159,12 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
     for (int k = 0; k < L; ++k) {
       const int C = S::W(k), N = S::W(k + 1);
       float* w = wp; float* wt = wp + C * N; float* b = wp + 2 * C * N;
-      for (int i = lane; i < C * N; i += 32) {
+      for (int i = tid; i < C * N; i += kThreads) {
         const float v = __ldg(p.w[k] + i);
         w[i] = v;
         wt[(i % C) * N + i / C] = v;
       }
-      for (int i = lane; i < N; i += 32) b[i] = __ldg(p.b[k] + i);
+      for (int i = tid; i < N; i += kThreads) b[i] = __ldg(p.b[k] + i);
       q.w[k] = w; q.wt[k] = wt; q.b[k] = b;
       wp += 2 * C * N + N;
     }
@@ -183,11 +172,12 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
 #pragma unroll
     for (int k = 0; k <= L; ++k) { q.h[k] = hp; hp += 32 * (S::W(k) + kPad); }
   }
-  __syncwarp();
   constexpr int d = S::W0 / 2;
+  constexpr int Q0 = S::W0 / kWarps;        // columns of the gathered row per warp (a piece of one table's row)
 
   const int64_t ntiles = (p.B + 31) / 32;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();   // weights staged (first pass) / the previous tile's rows are no longer read
     const int64_t row = tile * 32 + lane;
     const bool valid = row < p.B;
     int64_t u = -1, it = -1;
@@ -198,12 +188,14 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
       if (u < 0 || u >= p.U || it < 0 || it >= p.I) { u = -1; bad = true; }
     }
     const bool ok = u >= 0;
-    // ---- gather into the lane's own row ----------------------------------------------------------------
+    // ---- gather: the warp's piece of the lane's row ---------------------------------------------------------
     float* h0 = q.h[0] + lane * (S::W0 + kPad);
+    {
+      const int c0 = warp * Q0;                       // [0, d): user row, [d, 2d): item row
+      const float* src = (c0 < d) ? p.eum + (ok ? u : 0) * d + c0 : p.eim + (ok ? it : 0) * d + (c0 - d);
 #pragma unroll
-    for (int c = 0; c < d; c += 4) {
-      *reinterpret_cast<float4*>(h0 + c) = ok ? ldg4(p.eum + u * d + c) : make_float4(0, 0, 0, 0);
-      *reinterpret_cast<float4*>(h0 + d + c) = ok ? ldg4(p.eim + it * d + c) : make_float4(0, 0, 0, 0);
+      for (int c = 0; c < Q0; c += 4)
+        *reinterpret_cast<float4*>(h0 + c0 + c) = ok ? ldg4(src + c) : make_float4(0, 0, 0, 0);
     }
     float gu[kF], gi[kF];
 #pragma unroll
@@ -213,14 +205,22 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
       gu[c] = a.x; gu[c + 1] = a.y; gu[c + 2] = a.z; gu[c + 3] = a.w;
       gi[c] = b4.x; gi[c + 1] = b4.y; gi[c + 2] = b4.z; gi[c + 3] = b4.w;
     }
-    // ---- tower forward ------------------------------------------------------------------------------------
-    fwd_layer<S::W(0), S::W(1)>(h0, q.wt[0], q.b[0], q.h[1] + lane * (S::W(1) + kPad));
-    if constexpr (L >= 2)
-      fwd_layer<S::W(1), S::W(2)>(q.h[1] + lane * (S::W(1) + kPad), q.wt[1], q.b[1], q.h[2] + lane * (S::W(2) + kPad));
-    if constexpr (L >= 3)
-      fwd_layer<S::W(2), S::W(3)>(q.h[2] + lane * (S::W(2) + kPad), q.wt[2], q.b[2], q.h[3] + lane * (S::W(3) + kPad));
+    __syncthreads();
+    // ---- tower forward: every warp computes a quarter of each layer's outputs for its lane's sample ---------------
+    fwd_part<S::W(0), S::W(1), S::W(1) / kWarps>(h0, q.wt[0], q.b[0], q.h[1] + lane * (S::W(1) + kPad), warp * (S::W(1) / kWarps));
+    __syncthreads();
+    if constexpr (L >= 2) {
+      fwd_part<S::W(1), S::W(2), S::W(2) / kWarps>(q.h[1] + lane * (S::W(1) + kPad), q.wt[1], q.b[1],
+                                                   q.h[2] + lane * (S::W(2) + kPad), warp * (S::W(2) / kWarps));
+      __syncthreads();
+    }
+    if constexpr (L >= 3) {
+      fwd_part<S::W(2), S::W(3), S::W(3) / kWarps>(q.h[2] + lane * (S::W(2) + kPad), q.wt[2], q.b[2],
+                                                   q.h[3] + lane * (S::W(3) + kPad), warp * (S::W(3) / kWarps));
+      __syncthreads();
+    }
     const float* hL = q.h[L] + lane * (kF + kPad);
-    // ---- predict layer ------------------------------------------------------------------------------------------
+    // ---- predict layer (every warp computes it for its lane: 16 FMAs, no hand-off needed) -----------------------------
     float x = __ldg(p.pb);
     if (has_gmf) {
 #pragma unroll
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
 #pragma unroll
     for (int c = 0; c < kF; ++c) x = fmaf(__ldg(p.pw + mlp_off + c), hL[c], x);
     if (bad) x = __int_as_float(0x7fc00000);   // out-of-range index: NaN
-    if (valid && p.logits != nullptr) p.logits[row] = x;
+    if (warp == 0 && valid && p.logits != nullptr) p.logits[row] = x;
     if (!TRAIN) continue;
 
     // ---- loss and dloss/dlogit -------------------------------------------------------------------------------------
@@ -250,28 +250,30 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
         dl = (sig - y) * p.invB;
       }
     }
-    {
+    if (warp == 0) {
       const float ls_w = warp_sum(ls), dl_w = warp_sum(dl);
       if (lane == 0) {
         if (p.loss_accum != nullptr && p.dlogit_in == nullptr) atomicAdd(p.loss_accum, (double)ls_w * (double)p.invB);
         atomicAdd(p.gt + p.pb_off, dl_w);
       }
     }
-    // predict-weight gradient: sum over the warp's samples of dl * feature
-    if (has_gmf) {
+    // predict-weight gradient: sum over the tile's samples of dl * feature (warp 1: GMF half, warp 2: tower half)
+    if (warp == 1 && has_gmf) {
 #pragma unroll
       for (int c = 0; c < kF; ++c) {
         const float s = warp_sum(dl * gu[c] * gi[c]);
         if (lane == 0) atomicAdd(p.gt + p.pw_off + c, s);
       }
     }
+    if (warp == 2) {
 #pragma unroll
-    for (int c = 0; c < kF; ++c) {
-      const float s = warp_sum(dl * hL[c]);
-      if (lane == 0) atomicAdd(p.gt + p.pw_off + mlp_off + c, s);
+      for (int c = 0; c < kF; ++c) {
+        const float s = warp_sum(dl * hL[c]);
+        if (lane == 0) atomicAdd(p.gt + p.pw_off + mlp_off + c, s);
+      }
     }
-    // GMF branch: embedding-row gradients
-    if (has_gmf && ok) {
+    // GMF branch: embedding-row gradients (warp 3)
+    if (warp == 3 && has_gmf && ok) {
 #pragma unroll
       for (int c = 0; c < kF; c += 4) {
         const float4 w = ldg4(p.pw + c);
@@ -283,52 +285,59 @@ __global__ void __launch_bounds__(32) ncf_small_tile_kernel(const TileParams p) 
     float* dA = d_sm;
     float* dB = d_sm + S::delta();
     {
-      float* dr = dA + lane * (kF + kPad);          // delta_L
+      float* dr = dA + lane * (kF + kPad);          // delta_L: the warp's two columns
 #pragma unroll
-      for (int c = 0; c < kF; ++c) dr[c] = hL[c] > 0.f ? dl * __ldg(p.pw + mlp_off + c) : 0.f;
+      for (int c = warp * (kF / kWarps); c < (warp + 1) * (kF / kWarps); ++c)
+        dr[c] = hL[c] > 0.f ? dl * __ldg(p.pw + mlp_off + c) : 0.f;
     }
-    __syncwarp();
+    __syncthreads();
 #define NCF_SMALL_BACK(K)                                                                                          \
     if constexpr (L > K) {                                                                                          \
       constexpr int k = L - 1 - K;                               /* layer index, from the top */                    \
       constexpr int C = S::W(k), N = S::W(k + 1);                                                                   \
       float* din = (K & 1) ? dB : dA;                                                                               \
       float* dout = (K & 1) ? dA : dB;                                                                              \
-      wgrad_layer<C, N>(din, q.h[k], p.gt + p.w_off[k], p.gt + p.b_off[k], lane);                                   \
-      __syncwarp();                                              /* every lane is done reading every row */       \
-      if constexpr (k > 0) {                                                                                        \
-        bwd_layer<C, N, true>(din + lane * (N + kPad), q.w[k], q.h[k] + lane * (C + kPad), dout + lane * (C + kPad)); \
-      } else {                                                                                                      \
-        bwd_layer<C, N, false>(din + lane * (N + kPad), q.w[k], nullptr, h0);     /* dx_0 over the lane's input row */ \
+      wgrad_part<C, N>(din, q.h[k], p.gt + p.w_off[k], lane, warp * (C / kWarps));                                  \
+      if (warp == 0) {                                           /* bias gradient: column sums of delta */          \
+        for (int n = lane; n < N; n += 32) {                                                                        \
+          float sum = 0.f;                                                                                          \
+          for (int s2 = 0; s2 < 32; ++s2) sum += din[s2 * (N + kPad) + n];                                          \
+          atomicAdd(p.gt + p.b_off[k] + n, sum);                                                                    \
+        }                                                                                                           \
       }                                                                                                             \
-      __syncwarp();                                                                                                 \
+      __syncthreads();                                           /* every thread is done reading every row */     \
+      if constexpr (k > 0) {                                                                                        \
+        bwd_part<C, N, C / kWarps, true>(din + lane * (N + kPad), q.w[k], q.h[k] + lane * (C + kPad),               \
+                                         dout + lane * (C + kPad), warp * (C / kWarps));                            \
+      } else {                                                   /* dx_0 over the lane's input row */               \
+        bwd_part<C, N, C / kWarps, false>(din + lane * (N + kPad), q.w[k], nullptr, h0, warp * (C / kWarps));       \
+      }                                                                                                             \
+      __syncthreads();                                                                                              \
     }
     NCF_SMALL_BACK(0)
     NCF_SMALL_BACK(1)
     NCF_SMALL_BACK(2)
 #undef NCF_SMALL_BACK
-    // ---- scatter dx_0 into the MLP embedding-gradient rows ----------------------------------------------------------------
+    // ---- scatter dx_0 into the MLP embedding-gradient rows: the warp's piece of the lane's row ------------------------------
     if (ok) {
+      const int c0 = warp * Q0;
+      float* dst = (c0 < d) ? p.gum + u * d + c0 : p.gim + it * d + (c0 - d);
 #pragma unroll
-      for (int c = 0; c < d; c += 4) {
-        red_add4(p.gum + u * d + c, *reinterpret_cast<const float4*>(h0 + c));
-        red_add4(p.gim + it * d + c, *reinterpret_cast<const float4*>(h0 + d + c));
-      }
+      for (int c = 0; c < Q0; c += 4) red_add4(dst + c, *reinterpret_cast<const float4*>(h0 + c0 + c));
     }
-    __syncwarp();
   }
 }
 
 template <int L, bool TRAIN>
 int launch(const TileParams& p, cudaStream_t st) {
   const int64_t ntiles = (p.B + 31) / 32;
-  int64_t grid = (int64_t)ncf::num_sms() * 16;
+  int64_t grid = (int64_t)ncf::num_sms() * 8;
   if (grid > ntiles) grid = ntiles;
   using S = Shape<L>;
   const size_t smem = sizeof(float) * (S::weights() + S::acts() + (TRAIN ? 2 * S::delta() : 0));
   auto kern = ncf_small_tile_kernel<L, TRAIN>;
   if (smem > 48 * 1024) NCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(int)grid, 32, smem, st>>>(p);
+  kern<<<(int)grid, kThreads, smem, st>>>(p);
   NCF_LAUNCH_CHECK("ncf_small_tile_kernel");
   return NCF_OK;
 }
