@@ -7,54 +7,15 @@
 //   m <- m + (1-b1)(g - m);  v <- b2 v + (1-b2) g^2
 //   p <- p - (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // A row whose gradient is zero at step s still moves: m <- b1 m, v <- b2 v, same p update.
+#include <math.h>
+
+#include "adam_math.cuh"
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-// Zero-gradient steps replayed exactly per row.  The per-step term decays like
-// (b1/sqrt(b2))^j ~ 0.9005^j, so what is dropped beyond 160 steps is < 1e-7 of the first term.
-constexpr int kMaxReplay = 160;
-
-struct AdamConst {
-  float lr, b1, b2, eps, ln_b1, ln_b2, sqrt_b2;
-};
-
-__device__ __forceinline__ float bias_c1(const AdamConst& c, float s) {  // lr / (1 - b1^s)
-  return c.lr / (-expm1f(s * c.ln_b1));
-}
-__device__ __forceinline__ float bias_c2(const AdamConst& c, float s) {  // 1 / sqrt(1 - b2^s)
-  return 1.f / sqrtf(-expm1f(s * c.ln_b2));
-}
-
-// Brings one element from "state after step `last`" to "state after step last+gap" under zero
-// gradient.  c1s / c2s hold the bias terms of steps last+1 .. last+min(gap, kMaxReplay).
-__device__ __forceinline__ void replay_zero_steps(float& p, float& m, float& v, int gap,
-                                                  const float* c1s, const float* c2s,
-                                                  const AdamConst& c) {
-  if (gap <= 0) return;
-  const int n = min(gap, kMaxReplay);
-  const float m0 = m, v0 = v;
-  float mm = m0, r = sqrtf(v0);
-  if (m0 != 0.f) {
-    for (int j = 0; j < n; ++j) {
-      mm *= c.b1;
-      r *= c.sqrt_b2;
-      p -= c1s[j] * __fdividef(mm, fmaf(r, c2s[j], c.eps));
-    }
-  }
-  m = m0 * expf((float)gap * c.ln_b1);
-  v = v0 * expf((float)gap * c.ln_b2);
-}
-
-__device__ __forceinline__ void adam_real_step(float& p, float& m, float& v, float g, float c1t,
-                                               float c2t, const AdamConst& c) {
-  m = fmaf(1.f - c.b1, g - m, m);
-  v = fmaf(c.b2, v, (1.f - c.b2) * g * g);
-  p -= c1t * (m / fmaf(sqrtf(v), c2t, c.eps));
-}
-
 // One warp updates one table row of `dim` floats.  g == nullptr => replay only (flush).
 template <int V>
 __device__ __forceinline__ void adam_row(float* __restrict__ P, float* __restrict__ M,
@@ -317,6 +278,60 @@ __global__ void mark_rows_kernel(const int64_t* __restrict__ user, const int64_t
   }
 }
 
+// ncf_adam_prepare as ONE launch: a warp takes one (sample, side) of the batch; lane 0 registers the row in the
+// touched list, and the warp that won the registration replays the row's pending zero-gradient Adam steps right
+// away (lanes across the row, as in adam_rows_kernel<2>) instead of leaving that to a second kernel that walks
+// the list.  At the reference's batch of 256 the second launch was a quarter of the optimiser's time.
+__global__ void __launch_bounds__(kThreads) mark_catchup_kernel(const RowsParams q, const int64_t* __restrict__ user,
+                                                                const int64_t* __restrict__ item, int64_t B,
+                                                                int64_t* ulist, int64_t* ilist, int32_t* tcount) {
+  __shared__ float c1_sm[kWarps][kMaxReplay];
+  __shared__ float c2_sm[kWarps][kMaxReplay];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* c1s = c1_sm[warp];
+  float* c2s = c2_sm[warp];
+  const int64_t t = *q.step;   // rows are brought to "after step t"
+  const bool vec = ((q.f & 3) == 0) && ((q.d & 3) == 0);
+  const int64_t wid = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  for (int64_t e = wid; e < 2 * B; e += nw) {
+    const int64_t b = e >> 1;
+    const int side = (int)(e & 1);
+    const int64_t u = user[b], it = item[b];
+    if (u < 0 || u >= q.rows[0] || it < 0 || it >= q.rows[1]) continue;   // same rule as mark_rows_kernel
+    const int64_t r = side ? it : u;
+    int32_t last = 0;
+    if (lane == 0) {
+      if (atomicExch(&q.flag[side][r], 1) == 0) {
+        (side ? ilist : ulist)[atomicAdd(&tcount[side], 1)] = r;
+        last = q.last[side][r];
+        if (last >= t) last = 0;
+      }
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last <= 0) continue;   // lost the registration, never stepped, or current already
+    const int gap = (int)(t - last);
+    __syncwarp();
+    const int n = min(gap, kMaxReplay);
+    for (int j = lane; j < n; j += 32) {
+      const float sj = (float)(last + 1 + j);
+      c1s[j] = bias_c1(q.c, sj);
+      c2s[j] = bias_c2(q.c, sj);
+    }
+    __syncwarp();
+    if (q.has_gmf) {
+      const int64_t o = r * q.f;
+      if (vec) adam_row<4>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, nullptr, q.f, gap, c1s, c2s, 0.f, 0.f, q.c, lane);
+      else adam_row<1>(q.p_gmf[side] + o, q.m_gmf[side] + o, q.v_gmf[side] + o, nullptr, q.f, gap, c1s, c2s, 0.f, 0.f, q.c, lane);
+    }
+    if (q.has_mlp) {
+      const int64_t o = r * q.d;
+      if (vec) adam_row<4>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, nullptr, q.d, gap, c1s, c2s, 0.f, 0.f, q.c, lane);
+      else adam_row<1>(q.p_mlp[side] + o, q.m_mlp[side] + o, q.v_mlp[side] + o, nullptr, q.d, gap, c1s, c2s, 0.f, 0.f, q.c, lane);
+    }
+    if (lane == 0) q.last[side][r] = (int32_t)t;
+  }
+}
+
 // One side only (users or items): rows[] need not pair up with anything (row-sharded tables: a
 // rank registers its own users and, separately, the item rows other ranks asked it for).
 __global__ void mark_side_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t limit,
@@ -344,22 +359,6 @@ struct FlatParams {
   const int64_t* step;
   AdamConst c;
 };
-
-__device__ __forceinline__ void replay_inline(float& p, float& m, float& v, int last, int gap, const AdamConst& c) {
-  const int n = min(gap, kMaxReplay);
-  const float m0 = m, v0 = v;
-  float mm = m0, r = sqrtf(v0);
-  if (m0 != 0.f) {
-    for (int j = 0; j < n; ++j) {
-      const float s = (float)(last + 1 + j);
-      mm *= c.b1;
-      r *= c.sqrt_b2;
-      p -= bias_c1(c, s) * __fdividef(mm, fmaf(r, bias_c2(c, s), c.eps));
-    }
-  }
-  m = m0 * expf((float)gap * c.ln_b1);
-  v = v0 * expf((float)gap * c.ln_b2);
-}
 
 __global__ void __launch_bounds__(256) adam_flat_kernel(const FlatParams q) {
   // One index space over the four tables, so that every CTA streams the same number of float4s whatever the
@@ -478,14 +477,7 @@ int rows_grid(int64_t rows) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-AdamConst make_const(NcfAdamHyper h) {
-  AdamConst c;
-  c.lr = h.lr; c.b1 = h.beta1; c.b2 = h.beta2; c.eps = h.eps;
-  c.ln_b1 = (float)log((double)h.beta1);
-  c.ln_b2 = (float)log((double)h.beta2);
-  c.sqrt_b2 = (float)sqrt((double)h.beta2);
-  return c;
-}
+AdamConst make_const(NcfAdamHyper h) { return make_adam_const(h.lr, h.beta1, h.beta2, h.eps); }
 
 void fill_rows(RowsParams& q, const NcfModel* m, const NcfGrads* g, const NcfAdamState* s) {
   q.p_gmf[0] = m->embed_user_gmf; q.p_gmf[1] = m->embed_item_gmf;
@@ -691,12 +683,13 @@ extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfA
   if ((rc = check_state(m, s)) != NCF_OK) return rc;
   NCF_REQUIRE(B > 0 && user && item, "ncf_adam_prepare: empty batch or null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = launch_mark(m, g, user, item, B, st)) != NCF_OK) return rc;
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);
-  adam_rows_kernel<2><<<rows_grid(g_rows_hint), kThreads, 0, st>>>(q);
-  NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
+  mark_catchup_kernel<<<rows_grid(2 * B), kThreads, 0, st>>>(q, user, item, B, g->user_list, g->item_list,
+                                                             g->touched_count);
+  NCF_LAUNCH_CHECK("mark_catchup_kernel");
+  g_rows_hint += 2 * B;
   return NCF_OK;
 }
 

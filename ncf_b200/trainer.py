@@ -74,6 +74,7 @@ class FusedTrainStep:
             nb = ops.forward_workspace_bytes(teacher.abi_struct(), self.max_batch)
             self.teacher_workspace = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
         self._dirty = False  # True while some rows lag behind the dense-Adam state
+        self.fused_prepare = True  # False: ncf_mark_rows + ncf_adam_catchup instead of ncf_adam_prepare (tests)
         # Adam over every row instead of the touched rows once a step touches this share of the tables
         # (expected distinct rows of a uniform batch; NCF_ADAM_DENSE=0/1 forces a mode)
         self.dense_share = 0.42
@@ -112,8 +113,12 @@ class FusedTrainStep:
             # rows this batch reads must first catch up with the dense-Adam trajectory — unless every
             # row is current already (the previous steps ran the optimiser over all rows)
             if self._dirty or not dense:
-                ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
-                                 self.betas[1], self.eps)
+                if self.fused_prepare:   # registration + catch-up as one launch
+                    ops.adam_prepare(self._m, self._g, self._s, user, item, self.lr, self.betas[0],
+                                     self.betas[1], self.eps)
+                else:                    # the same as two: list first, then a walk over the list
+                    ops.mark_rows(self._m, self._g, user, item)
+                    ops.adam_catchup(self._m, self._g, self._s, self.lr, self.betas[0], self.betas[1], self.eps)
         else:
             ops.mark_rows(self._m, self._g, user, item)
         if self.kd is None:

@@ -173,6 +173,66 @@ def test_lazy_adam_equals_dense_oracle_over_long_gaps():
         assert_close_adam(got[k], params[k], k, rtol=2e-4, outlier_frac=5e-3, outlier_rtol=5e-3)
 
 
+@pytest.mark.parametrize("model_type,f,L,B", [("NeuMF-end", 8, 3, 256), ("NeuMF-end", 32, 3, 4096),
+                                               ("NeuMF-end", 6, 2, 100), ("GMF", 16, 1, 33), ("MLP", 8, 2, 1000)])
+def test_one_launch_prepare_equals_mark_then_catch_up(model_type, f, L, B):
+    """ncf_adam_prepare (rows registered and replayed by one kernel) == ncf_mark_rows + ncf_adam_catchup, bit for
+    bit, on a state with gaps on both sides of the exact-replay window, rows never stepped and rows already
+    current; ids outside the tables are skipped by both."""
+    from ncf_b200 import ops
+    from ncf_b200.models import NCF
+    from ncf_b200.trainer import FusedTrainStep
+    torch.manual_seed(5)
+    U, I, t_now = 700, 500, 400
+    pair = []
+    for _ in range(2):
+        torch.manual_seed(5)
+        model = NCF(U, I, f, L, 0.0, model_type).to(dev())
+        ts = FusedTrainStep(model, optimizer="adam", lr=1e-3, max_batch=B)
+        gen = torch.Generator(device="cpu").manual_seed(11)
+        for name in ("m_user_gmf", "m_item_gmf", "m_user_mlp", "m_item_mlp", "v_user_gmf", "v_item_gmf",
+                     "v_user_mlp", "v_item_mlp"):
+            buf = getattr(ts.state, name)
+            if buf is None:
+                continue
+            x = torch.randn(buf.shape, generator=gen) * 1e-3
+            buf.copy_((x * x if name.startswith("v_") else x).to(dev()))
+        for name, n in (("user_last_step", U), ("item_last_step", I)):
+            last = torch.randint(1, t_now + 1, (n,), generator=gen, dtype=torch.int32)
+            last[torch.rand(n, generator=gen) < 0.1] = 0          # never stepped
+            last[torch.rand(n, generator=gen) < 0.1] = t_now      # current already
+            getattr(ts.state, name).copy_(last.to(dev()))
+        ts.state.step.fill_(t_now)
+        pair.append((model, ts))
+    gen = torch.Generator(device="cpu").manual_seed(12)
+    user = torch.randint(0, U, (B,), generator=gen)
+    item = torch.randint(0, I, (B,), generator=gen)
+    user[3], item[5] = U, -1                                      # samples 3 and 5 are not registered at all
+    user, item = user.to(dev()), item.to(dev())
+    (ma, ta), (mb, tb) = pair
+    ops.adam_prepare(ta._m, ta._g, ta._s, user, item, 1e-3)
+    ops.mark_rows(tb._m, tb._g, user, item)
+    ops.adam_catchup(tb._m, tb._g, tb._s, 1e-3)
+    torch.cuda.synchronize()
+    sa, sb = state_np(ma), state_np(mb)
+    for k in sb:
+        assert np.array_equal(sa[k], sb[k]), k
+    for name, _ in ops.NcfAdamState._fields_:
+        x, y = getattr(ta.state, name), getattr(tb.state, name)
+        if x is not None:
+            assert torch.equal(x, y), name
+    assert torch.equal(ta.grads.user_flag, tb.grads.user_flag) and torch.equal(ta.grads.item_flag, tb.grads.item_flag)
+    na, nb = ta.grads.touched_count.tolist(), tb.grads.touched_count.tolist()
+    assert na == nb
+    keep = torch.ones(B, dtype=torch.bool)
+    keep[3] = keep[5] = False
+    assert sorted(ta.grads.user_list[:na[0]].tolist()) == sorted(set(user.cpu()[keep].tolist()))
+    assert sorted(ta.grads.item_list[:na[1]].tolist()) == sorted(set(item.cpu()[keep].tolist()))
+    assert sorted(tb.grads.item_list[:nb[1]].tolist()) == sorted(ta.grads.item_list[:na[1]].tolist())
+    # and the catch-up did something: rows of the batch with a pending gap are now stamped t_now
+    assert int((ta.state.user_last_step[user.clamp(0, U - 1)[keep.to(dev())]] == t_now).sum()) > B // 2
+
+
 def test_kd_response_matches_reference():
     from ncf_b200.trainer import FusedTrainStep
     z, meta = load_golden("kd_response")
