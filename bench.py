@@ -536,12 +536,15 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     dense = ts.dense_adam(B * world)
     umma = B >= 8192 and f >= 32
     # kernels per step (replayed from a CUDA graph or launched one by one, the same kernels):
-    # shuffle_epoch + [mark, catch-up] + (images, tower, wgrad | split, tile) + (flat, stamp | rows) + tower Adam + finalize
-    launches_per_step = 1 + (0 if dense else 2) + (3 if umma else 2) + (2 if dense else 1) + 2
+    # shuffle_epoch + [prepare] + (images, tower, wgrad | split, tile) + (flat, stamp | rows); the tower's Adam
+    # update and the step counter are folded into the last of them
+    launches_per_step = 1 + (0 if dense else 1) + (3 if umma else 2) + (2 if dense else 1)
     if dp is not None and not dp.partition_users and dp.sharded is not None:
-        launches_per_step = 1 + 3 + 3       # images, tower, wgrad, adam_range (or adam_p2p), stamp, finalize
+        launches_per_step = 1 + 3 + 2       # images, tower, wgrad, adam_range (or adam_p2p), stamp
     if dp is not None and dp.tail is not None:
-        launches_per_step = 1 + 3 + 1 + 3   # shuffle, images, tower, wgrad, adam_p2p, adam_flat (users), stamp, finalize
+        launches_per_step = 1 + 3 + 1 + 2   # shuffle, images, tower, wgrad, adam_p2p, adam_flat (users), stamp
+        if getattr(dp.tail["barrier"], "__self__", None).__class__.__name__ == "PeerBarrier":
+            launches_per_step += 2          # the two peer-memory rank barriers around adam_p2p
 
     # materialise the timed batches once more for the per-phase and end-to-end passes
     bu = torch.empty(need, dtype=torch.int64, device=dev)

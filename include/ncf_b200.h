@@ -85,7 +85,7 @@ typedef struct NcfGrads {
   int32_t* item_flag;     /* [item_num] 0/1 */
   int64_t* user_list;     /* capacity >= max distinct users per optimiser step */
   int64_t* item_list;
-  int32_t* touched_count; /* [2]: {n_user_rows, n_item_rows} */
+  int32_t* touched_count; /* [4]: {n_user_rows, n_item_rows, ticket of the step-closing kernel (zero between calls), reserved} */
 } NcfGrads;
 
 /* Adam state (reference optim.Adam defaults, scripts/train_neumf.py:90).  The reference Adam is

@@ -32,6 +32,9 @@ __device__ __forceinline__ void replay_zero_steps(float& p, float& m, float& v, 
   const float m0 = m, v0 = v;
   float mm = m0, r = sqrtf(v0);
   if (m0 != 0.f) {
+    // the terms are independent but for mm, r and the running p: unrolled, their table loads and reciprocals
+    // overlap (a row 160 steps behind is the critical path of a small-batch step)
+#pragma unroll 4
     for (int j = 0; j < n; ++j) {
       mm *= c.b1;
       r *= c.sqrt_b2;

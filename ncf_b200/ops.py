@@ -299,7 +299,7 @@ class GradBuffers:
         return GradBuffers(
             *pieces, z(user_num, dt=torch.int32), z(item_num, dt=torch.int32),
             z(min(capacity, user_num), dt=torch.int64), z(min(capacity, item_num), dt=torch.int64),
-            z(2, dt=torch.int32), flat)
+            z(4, dt=torch.int32)[:2], flat)   # + the ticket word of the step-closing kernels behind the counts
 
     def struct(self) -> NcfGrads:
         g = NcfGrads()
