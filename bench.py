@@ -701,7 +701,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
             hf.launch()
             j = (k + 1) % nb
             hf.prefetch(hu[sl(j)], hi[sl(j)], hl[sl(j)])   # overlaps with the step just launched
-            return hf.wait()                                # the reference reads loss.item() every step
+            # the reference reads loss.item() every step: so do we, one step behind, so that the GPU already has
+            # step k queued while the host reads the loss of step k-1 (the last one is read before the clock stops)
+            return hf.wait() if hf.in_flight == 2 else None
         du.copy_(hu[sl(k)], non_blocking=True)
         di.copy_(hi[sl(k)], non_blocking=True)
         dl.copy_(hl[sl(k)], non_blocking=True)
@@ -719,6 +721,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     t0 = time.perf_counter()
     for k in range(W, W + K):
         e2e_step(k)
+    if hf is not None:
+        while hf.in_flight:
+            hf.wait()
     barrier()
     clocks = sampler.stop()     # sampled from the start of the device-resident region to the end of the end-to-end one
     if world > 1:               # every rank watched its own GPU: keep the slowest one in view as well
@@ -849,7 +854,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         roofline["dp_in_place"] = dp_in_place
 
     e2e_launch = ("HostFedTrainer: cuda-graph step" + (" (NCCL all-reduce captured)" if dp is not None else "")
-                  + ", next batch H2D overlapped") if used_graph else "eager"
+                  + ", next batch H2D overlapped, loss read one step behind") if used_graph else "eager"
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 unsampled=unsampled,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,

@@ -221,6 +221,14 @@ class HostFedTrainer:
 
         hf = HostFedTrainer(ts, batch); hf.prefetch(*b[0])
         for k in range(n): hf.prefetch(*b[k + 1]); loss = hf.step()
+
+    `launch()` / `wait()` split the step so that the GPU never waits for the host: up to two steps may be in
+    flight, and `wait()` returns the loss of the oldest one (the reference only sums the losses for its log
+    line, so reading step k's loss while step k+1 runs changes nothing):
+
+        hf.prefetch(*b[0]); hf.launch(); hf.prefetch(*b[1])
+        for k in range(1, n): hf.launch(); hf.prefetch(*b[k + 1]); loss = hf.wait()    # loss of step k-1
+        loss = hf.wait()
     """
 
     def __init__(self, ts: FusedTrainStep, batch: int, step_fn=None):
@@ -233,15 +241,30 @@ class HostFedTrainer:
                       torch.empty(batch, dtype=torch.float32, device=dev)) for _ in range(2)]
         for b in self.bufs:  # valid indices for the capture pass
             b[0].zero_(); b[1].zero_(); b[2].zero_()
-        self.graphs = [ts.capture(*b, batch, step_fn) for b in self.bufs]
+        # each graph = clear the loss accumulator, the step, park the loss in the set's own device word: the
+        # read-back then runs on its own stream and the next step does not queue behind a PCIe round trip
+        base_step = step_fn or ts.step
+        self.loss_dev = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+
+        def recorded(j):
+            def fn(user, item, label):
+                ts.loss_accum.zero_()
+                base_step(user, item, label)
+                self.loss_dev[j].copy_(ts.loss_accum)
+            return fn
+        self.graphs = [ts.capture(*b, batch, recorded(j)) for j, b in enumerate(self.bufs)]
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.read_stream = torch.cuda.Stream(device=dev)
+        self.stepped = [torch.cuda.Event(), torch.cuda.Event()]
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
         for e in self.consumed:
             e.record()
-        self.host_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self.host_loss = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]   # loss of the step on buffer set j is in host_loss[j]
         self.n_staged = 0   # batches staged so far
-        self.n_run = 0      # batches trained so far
+        self.n_run = 0      # batches trained (launched) so far
+        self.n_waited = 0   # losses handed back so far
 
     def prefetch(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor) -> None:
         if self.n_staged - self.n_run >= 2:
@@ -261,18 +284,31 @@ class HostFedTrainer:
         """Enqueues the step on the oldest staged batch and the read-back of its loss."""
         if self.n_run >= self.n_staged:
             raise _lib.NcfError("HostFedTrainer.step: no staged batch")
+        if self.n_run - self.n_waited >= 2:
+            raise _lib.NcfError("HostFedTrainer.launch: two steps are in flight, wait() for the older one first")
         j = self.n_run & 1
         cur = torch.cuda.current_stream()
         cur.wait_event(self.copied[j])
-        self.ts.loss_accum.zero_()
         self.graphs[j].replay()
         self.consumed[j].record()
-        self.host_loss.copy_(self.ts.loss_accum, non_blocking=True)
+        with torch.cuda.stream(self.read_stream):
+            self.read_stream.wait_event(self.consumed[j])
+            self.host_loss[j:j + 1].copy_(self.loss_dev[j], non_blocking=True)
+            self.done[j].record(self.read_stream)
         self.n_run += 1
 
     def wait(self) -> float:
-        torch.cuda.current_stream().synchronize()
-        return float(self.host_loss[0])
+        """Loss of the oldest step whose loss has not been read yet (blocks until that step is complete)."""
+        if self.n_waited >= self.n_run:
+            raise _lib.NcfError("HostFedTrainer.wait: no step in flight")
+        j = self.n_waited & 1
+        self.done[j].synchronize()
+        self.n_waited += 1
+        return float(self.host_loss[j])
+
+    @property
+    def in_flight(self) -> int:
+        return self.n_run - self.n_waited
 
     def step(self) -> float:
         self.launch()

@@ -96,9 +96,11 @@ def test_tf32_tower_mode_within_stated_tolerance():
     assert 0 < err < 2e-3, err
 
 
-def test_host_fed_trainer_equals_eager_steps():
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_host_fed_trainer_equals_eager_steps(pipelined):
     """HostFedTrainer (graph-captured steps fed from pinned host batches through a copy stream)
-    follows the same trajectory as eager FusedTrainStep.step on device batches."""
+    follows the same trajectory as eager FusedTrainStep.step on device batches — also with two steps in
+    flight (the loss of step k read while step k+1 runs)."""
     import copy
     from ncf_b200.models import NCF
     from ncf_b200.trainer import FusedTrainStep, HostFedTrainer
@@ -124,7 +126,13 @@ def test_host_fed_trainer_equals_eager_steps():
         hf.launch()
         if k + 1 < T:
             hf.prefetch(*batches[k + 1])
+        if not pipelined or hf.in_flight == 2:
+            fed.append(hf.wait())
+    while hf.in_flight:
         fed.append(hf.wait())
+    with pytest.raises(Exception):
+        hf.wait()                      # nothing in flight any more
+    assert len(fed) == T
     for x, y in zip(eager, fed):
         assert abs(x - y) <= 1e-6 * abs(x)
     ta.flush(); tb.flush()
