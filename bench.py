@@ -423,7 +423,11 @@ def run_ours(args):
                 "launch": st["e2e_launch"],
                 "note": "value's timer is CUDA events on the stream, e2e's is the host clock around the same number of "
                         "steps; the two agree within run-to-run noise when the copies are hidden"},
-        "gpu_launches": st["launches_per_step"] * K,
+        # our kernels inside the timed region: per step everything but the shuffle, which lays out a whole window
+        "gpu_launches": (st["launches_per_step"] - 1) * K + K // st["window"],
+        "launch": (f"CUDA-graph windows of {st['window']} steps (one shuffle launch + one graph launch per window, as "
+                   f"ncf_b200.trainer.train_epoch runs an epoch)" if st["window"] > 1 else
+                   "one shuffle launch + one CUDA-graph launch per step"),
         "clocks": st["clocks"],
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -452,7 +456,13 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     from ncf_b200.trainer import EpochStream, FusedTrainStep
 
     shape, f, L, B = WORKLOADS[args.workload]
-    n_batches = W + K
+    # the timed steps run as CUDA-graph windows of G steps, the scheme ncf_b200.trainer.train_epoch uses (one
+    # shuffle launch lays out the G batches of a window, one graph launch runs its G steps): G = the largest
+    # divisor of K up to 64; NCF_BENCH_WINDOW=1 = one shuffle + one graph launch per step
+    G = int(os.environ.get("NCF_BENCH_WINDOW", "0")) or max(g for g in range(1, 65) if K % g == 0)
+    if args.no_graph or K % G:
+        G = 1
+    n_batches = W + K + (2 * G if G > 1 else 0)     # + one warm-up replay of each of the two window graphs
     need = n_batches * B
     inter = make_interactions(shape, device=dev)
     U, I = inter.user_num, inter.item_num
@@ -505,8 +515,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
 
     # ---- device-resident timing ------------------------------------------------------------------
     # the first warm-up steps run eagerly (they load every kernel), then the step over each of the two
-    # batch buffers is captured once (at N>1 with its NCCL all-reduce) and replayed: two launches per
-    # step from the host (shuffle + graph) - the same windows-of-graphs scheme train_epoch uses
+    # batch buffers is captured once (at N>1 with its exchange) and replayed; with G > 1 the timed region
+    # then runs windows of G steps (two window buffers, one graph each, each replayed once as warm-up)
     use_step_graph = not args.no_graph and (dp is None or (dp.partition_users and os.environ.get("NCF_DP_GRAPH", "1") != "0"))
     use_e2e_graph = use_step_graph
     if dp is not None and os.environ.get("NCF_BENCH_STEP_GRAPH", "1") == "0":
@@ -516,6 +526,25 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         if k == 1 and use_step_graph:
             barrier()
             graphs = [ts.capture(*bufs[j], B, step_fn if dp is not None else None) for j in range(2)]
+    wgraphs = None
+    if G > 1 and use_step_graph:
+        wbufs = [(torch.empty(G * B, dtype=torch.int64, device=dev), torch.empty(G * B, dtype=torch.int64, device=dev),
+                  torch.empty(G * B, dtype=torch.float32, device=dev)) for _ in range(2)]
+        for wb in wbufs:
+            stream.fill(q0, G * B, *wb)      # valid ids for the capture pass
+        barrier()
+        wgraphs = [ts.capture(*wbufs[j], B, step_fn if dp is not None else None) for j in range(2)]
+
+    def run_window(kw, first_step):
+        """Steps [first_step + kw*G, first_step + (kw+1)*G): one shuffle launch + one graph launch."""
+        u, i, y = wbufs[kw & 1]
+        stream.fill(q0 + (first_step + kw * G) * B, G * B, u, i, y)
+        wgraphs[kw & 1].replay()
+
+    if wgraphs is not None:
+        run_window(0, W)
+        run_window(1, W)
+    T0 = W + (2 * G if wgraphs is not None else 0)     # first timed step
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -524,11 +553,18 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # all eight ranks running ahead unsynchronised the steps were measured 8 % slower (0.543 vs 0.497 ms at N=8; at
     # N=2 graph replays cost the same either way: 0.394 vs 0.400 ms - profiles/r02/dp_loop_modes.md)
     sync_every = int(os.environ.get("NCF_BENCH_SYNC_EVERY", "4" if world > 1 else "0"))
+    def timed_steps():
+        if wgraphs is not None:
+            for kw in range(K // G):
+                run_window(kw, T0)
+            return
+        for k in range(W, W + K):
+            one_step(k)
+            if sync_every and (k - W + 1) % sync_every == 0:
+                torch.cuda.current_stream().synchronize()
+
     e0.record()
-    for k in range(W, W + K):
-        one_step(k)
-        if sync_every and (k - W + 1) % sync_every == 0:
-            torch.cuda.current_stream().synchronize()
+    timed_steps()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -745,10 +781,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         barrier()
         u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         u0.record()
-        for k in range(W, W + K):
-            one_step(k)
-            if sync_every and (k - W + 1) % sync_every == 0:
-                torch.cuda.current_stream().synchronize()
+        timed_steps()
         u1.record()
         barrier()
         ums = max_over_ranks(u0.elapsed_time(u1))
@@ -858,6 +891,7 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 unsampled=unsampled,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,
+                window=(G if wgraphs is not None else 1),
                 dp_partitioned=(dp.partition_users if dp is not None else True),
                 dp_tail=(dp is not None and dp.tail is not None))
 
