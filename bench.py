@@ -79,16 +79,19 @@ class ClockSampler:
     """SM clock and throttle reasons sampled through NVML (a thread per rank for its own GPU, every 5 ms)
     from the start of the device-resident timed region to the end of the end-to-end one (the GPU is under
     load throughout: timed steps, per-phase passes, host-fed steps) — the same fields as the nvidia-smi
-    clocks line of B200_PROFILING.md.  The polling is not free at N=8: the same loop ran at 0.375 ms/step
-    without it and 0.45 ms/step with it (per-rank pollers at 1 ms or 20 ms alike; one poller on rank 0 for
-    all eight GPUs: 0.56) — NVML queries from the ranks hold up launches that every other rank then waits
-    for at the step's barrier.  `value` is measured WITH the polling; the line also carries the same loop
-    without it (`unsampled_loop`)."""
+    clocks line of B200_PROFILING.md.  The polling itself costs nothing measurable, also at N=8
+    (profiles/r02/clock_sampling_experiment.md: 0.361 ms/step with no thread, an idle thread, either query,
+    both at 5 / 50 / 200 ms); what did cost 20 % in earlier runs was starting it (nvmlInit) between the
+    barrier and the first timed step, which let the ranks enter the timed region at different times.  The
+    line still carries the same loop after the samplers were stopped (`unsampled_loop`)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index, period=0.005):
+    def __init__(self, gpu_index, period=0.005, what="both", aligned=False):
+        """`what`: "both" | "clock" | "reasons" | "idle" (the thread wakes but asks nothing); `aligned`: polls at
+        multiples of the period on the machine's clock, i.e. at the same instants on every rank (experiments)."""
         self.period = float(os.environ.get("NCF_BENCH_CLOCK_PERIOD", period))
+        self.what, self.aligned = what, aligned
         self.gpu, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
         self._stop, self._thread, self._nvml = None, None, None
 
@@ -114,11 +117,17 @@ class ClockSampler:
         def loop():
             while not self._stop.is_set():
                 try:
-                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    if self.what in ("both", "clock"):
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    if self.what in ("both", "reasons"):
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     pass
-                self._stop.wait(self.period)
+                if self.aligned:
+                    now = time.time()
+                    self._stop.wait((int(now / self.period) + 1) * self.period - now)
+                else:
+                    self._stop.wait(self.period)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
@@ -546,8 +555,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         run_window(1, W)
     T0 = W + (2 * G if wgraphs is not None else 0)     # first timed step
     sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
+    sampler.start()     # BEFORE the barrier: nvmlInit takes a different time on every rank, and a rank that enters the
+    barrier()           # timed region late is waited for by all the others at the first exchange of the window
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # At N>1 the loop waits for the device every 4th step, as a loop that reads its loss every few steps does: with
     # all eight ranks running ahead unsynchronised the steps were measured 8 % slower (0.543 vs 0.497 ms at N=8; at
@@ -787,6 +796,34 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         ums = max_over_ranks(u0.elapsed_time(u1))
         unsampled = {"value": world * K * B / (ums * 1e-3), "ms_per_step": ums / K,
                      "note": "the timed loop repeated after the clock samplers were stopped"}
+
+    if dp is not None and os.environ.get("NCF_BENCH_CLOCK_EXPERIMENT") == "1":
+        # what exactly about the clock sampling slows the coupled ranks down: printed to stderr, not part of the line
+        out = {}
+        for name, kw in (("none", None), ("idle_thread_5ms", dict(what="idle")), ("clock_only_5ms", dict(what="clock")),
+                         ("reasons_only_5ms", dict(what="reasons")), ("both_5ms", dict()),
+                         ("both_5ms_aligned", dict(aligned=True)), ("both_50ms", dict(period=0.05)),
+                         ("both_200ms", dict(period=0.2)), ("none_again", None)):
+            smp = ClockSampler(local, **kw) if kw is not None else None
+            barrier()
+            if smp is not None:
+                smp.start()
+            time.sleep(0.3)
+            barrier()
+            best = None
+            for rep in range(3):
+                x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                x0.record()
+                timed_steps()
+                x1.record()
+                barrier()
+                ms = max_over_ranks(x0.elapsed_time(x1)) / K
+                best = ms if best is None else min(best, ms)
+            got = smp.stop() if smp is not None else None
+            out[name] = {"ms_per_step_best_of_3": best, "samples": got["samples"] if got else 0}
+        if rank == 0:
+            print("CLOCK_EXPERIMENT " + json.dumps(out), file=sys.stderr, flush=True)
 
     # ---- evaluation throughput (second half of the metric: eval users/s): every rank scores its own users ----
     from ncf_b200.metrics import evaluate
