@@ -736,6 +736,14 @@ extern "C" int ncf_adam_prepare(const NcfModel* m, const NcfGrads* g, const NcfA
   RowsParams q{};
   fill_rows(q, m, g, s);
   q.c = make_const(h);
+  if (B > 4096) {
+    // large batches: a thread per sample registers (one warp per sample-side would serialise 2B dependent
+    // chains on a few thousand resident warps), then a warp per DISTINCT row replays
+    if ((rc = launch_mark(m, g, user, item, B, st)) != NCF_OK) return rc;
+    adam_rows_kernel<2><<<rows_grid(g_rows_hint), kThreads, 0, st>>>(q, StepTail{});
+    NCF_LAUNCH_CHECK("adam_rows_kernel<catchup>");
+    return NCF_OK;
+  }
   mark_catchup_kernel<<<rows_grid(2 * B), kThreads, 0, st>>>(q, user, item, B, g->user_list, g->item_list,
                                                              g->touched_count);
   NCF_LAUNCH_CHECK("mark_catchup_kernel");

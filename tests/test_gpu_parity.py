@@ -173,7 +173,7 @@ def test_lazy_adam_equals_dense_oracle_over_long_gaps():
         assert_close_adam(got[k], params[k], k, rtol=2e-4, outlier_frac=5e-3, outlier_rtol=5e-3)
 
 
-@pytest.mark.parametrize("model_type,f,L,B", [("NeuMF-end", 8, 3, 256), ("NeuMF-end", 32, 3, 4096),
+@pytest.mark.parametrize("model_type,f,L,B", [("NeuMF-end", 8, 3, 256), ("NeuMF-end", 32, 3, 4096), ("NeuMF-end", 16, 2, 6000),
                                                ("NeuMF-end", 6, 2, 100), ("GMF", 16, 1, 33), ("MLP", 8, 2, 1000)])
 def test_one_launch_prepare_equals_mark_then_catch_up(model_type, f, L, B):
     """ncf_adam_prepare (rows registered and replayed by one kernel) == ncf_mark_rows + ncf_adam_catchup, bit for
