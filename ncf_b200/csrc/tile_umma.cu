@@ -1465,6 +1465,17 @@ umma_wgrad_kernel(const __grid_constant__ TileParams p, const __grid_constant__ 
 // ---- launchers ---------------------------------------------------------------------------------------------
 constexpr size_t kSmemBudget = 200 * 1024;
 
+// debug-only knobs, read once per process (the knobs tests flip at run time - NCF_UMMA_DISABLE, NCF_UMMA_FUSED,
+// NCF_UMMA_MIN_B - are read per call)
+static int ablate_knob() {
+  static const int v = [] { const char* e = getenv("NCF_UMMA_ABLATE"); return e ? atoi(e) : 0; }();
+  return v;
+}
+static bool timing_knob() {
+  static const bool v = getenv("NCF_UMMA_TIMING") != nullptr;
+  return v;
+}
+
 template <int EPI>
 int launch_gemm(const TileParams& p, GemmArgs g, int nblocks, cudaStream_t st) {
   const size_t stage = 2 * (size_t)kTile * 128 + 2 * (size_t)g.N * 128;
@@ -1475,7 +1486,7 @@ int launch_gemm(const TileParams& p, GemmArgs g, int nblocks, cudaStream_t st) {
     return NCF_ERR_ARG;
   }
   g.stages = stages;
-  if (const char* ab = getenv("NCF_UMMA_ABLATE")) g.ablate = atoi(ab);
+  g.ablate = ablate_knob();
   const size_t smem = stages * stage + 1024;
   auto kern = umma_gemm_kernel<EPI>;
   NCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1508,7 +1519,7 @@ int launch_gemm(const TileParams& p, GemmArgs g, int nblocks, cudaStream_t st) {
 int launch_wgrad(const TileParams& p, int passes, cudaStream_t st) {
   WgradArgs g{};
   g.passes = passes;
-  if (const char* ab = getenv("NCF_UMMA_ABLATE")) g.ablate = atoi(ab);
+  g.ablate = ablate_knob();
   // one job per [128 x 256] block of every layer's dW; CTAs shared out by operand bytes per sample
   double weight[12], total = 0;
   for (int k = 0; k < p.L; ++k) {
@@ -1579,7 +1590,7 @@ struct StepTimer {
   const char* name[32];
   int n = 0;
   static thread_local StepTimer* g_timer;
-  StepTimer(cudaStream_t s) : on(g_profile.enabled || getenv("NCF_UMMA_TIMING") != nullptr), st(s) {
+  StepTimer(cudaStream_t s) : on(g_profile.enabled || timing_knob()), st(s) {
     g_timer = this;
     mark("start");
   }
@@ -1657,7 +1668,7 @@ template <bool TRAIN>
 int launch_tower(const TileParams& p, int passes, cudaStream_t st) {
   TowerArgs g{};
   g.passes = passes;
-  if (const char* ab = getenv("NCF_UMMA_ABLATE")) g.ablate = atoi(ab);
+  g.ablate = ablate_knob();
   int col = 0;
   for (int k = 1; k <= p.L; ++k) {
     g.hcol[k] = col;
