@@ -465,14 +465,6 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     from ncf_b200.trainer import EpochStream, FusedTrainStep
 
     shape, f, L, B = WORKLOADS[args.workload]
-    # the timed steps run as CUDA-graph windows of G steps, the scheme ncf_b200.trainer.train_epoch uses (one
-    # shuffle launch lays out the G batches of a window, one graph launch runs its G steps): G = the largest
-    # divisor of K up to 64; NCF_BENCH_WINDOW=1 = one shuffle + one graph launch per step
-    G = int(os.environ.get("NCF_BENCH_WINDOW", "0")) or max(g for g in range(1, 65) if K % g == 0)
-    if args.no_graph or K % G:
-        G = 1
-    n_batches = W + K + (2 * G if G > 1 else 0)     # + one warm-up replay of each of the two window graphs
-    need = n_batches * B
     inter = make_interactions(shape, device=dev)
     U, I = inter.user_num, inter.item_num
     torch.manual_seed(0)
@@ -492,7 +484,26 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     # the epoch stream of this rank: negatives for its positives, shuffled, laid out window by window
     stream = EpochStream(pos_user, pos_item, U, I, num_ng=4, seed=20250605, p_offset=p_off)
     stream.begin_epoch(0)
-    q0 = 0 if (dp is not None and dp.partition_users) else rank * need
+    # the timed steps run as CUDA-graph windows of G steps, the scheme ncf_b200.trainer.train_epoch uses (one
+    # shuffle launch lays out the G batches of a window, one graph launch runs its G steps): G = the largest
+    # divisor of K up to 64 whose two warm-up windows still fit into this rank's epoch stream;
+    # NCF_BENCH_WINDOW=1 = one shuffle + one graph launch per step
+    own_stream = dp is None or dp.partition_users          # else: the ranks take consecutive slices of one stream
+    avail = stream.S // B // (1 if own_stream else world)  # steps this rank can draw from the epoch
+    if world > 1:                                          # every rank must capture the same windows
+        t_av = torch.tensor([avail], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_av, op=dist.ReduceOp.MIN)
+        avail = int(t_av.item())
+    want = int(os.environ.get("NCF_BENCH_WINDOW", "0"))
+    G = 1
+    if not args.no_graph:
+        for g in range(min(64, K), 0, -1):
+            if K % g == 0 and (want in (0, g)) and W + K + (2 * g if g > 1 else 0) <= avail:
+                G = g
+                break
+    n_batches = W + K + (2 * G if G > 1 else 0)     # + one warm-up replay of each of the two window graphs
+    need = n_batches * B
+    q0 = 0 if own_stream else rank * need
     if q0 + need > stream.S:
         raise SystemExit(f"workload too small for {n_batches} steps of {B} on {world} ranks")
     # two rotating device batches: step k reads buffer k%2 while nothing else touches it
