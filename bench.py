@@ -464,6 +464,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
     from ncf_b200.synth import make_interactions
     from ncf_b200.trainer import EpochStream, FusedTrainStep
 
+    import gc
+    gc.disable()      # no collector pauses inside the host-clocked regions (re-enabled by the caller's return)
     shape, f, L, B = WORKLOADS[args.workload]
     inter = make_interactions(shape, device=dev)
     U, I = inter.user_num, inter.item_num
@@ -748,7 +750,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])
             step_fn(du, di, dl)
         barrier()
-        hf = HostFedTrainer(ts, B, step_fn if dp is not None else None)   # at N>1 the all-reduce is captured too
+        # at N>1 the exchange is captured too; 8 buffer sets: the host may fall 3 ms behind before the GPU idles
+        hf = HostFedTrainer(ts, B, step_fn if dp is not None else None, depth=8)
         nb = W + K
         hf.prefetch(hu[sl(0)], hi[sl(0)], hl[sl(0)])
 
@@ -757,9 +760,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
             hf.launch()
             j = (k + 1) % nb
             hf.prefetch(hu[sl(j)], hi[sl(j)], hl[sl(j)])   # overlaps with the step just launched
-            # the reference reads loss.item() every step: so do we, one step behind, so that the GPU already has
-            # step k queued while the host reads the loss of step k-1 (the last one is read before the clock stops)
-            return hf.wait() if hf.in_flight == 2 else None
+            # the reference reads loss.item() every step: so do we, up to depth-1 steps behind, so that the GPU has
+            # the next steps queued while the host reads an older loss (the last ones are read before the clock stops)
+            return hf.wait() if hf.in_flight == hf.depth else None
         du.copy_(hu[sl(k)], non_blocking=True)
         di.copy_(hi[sl(k)], non_blocking=True)
         dl.copy_(hl[sl(k)], non_blocking=True)
@@ -935,7 +938,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         roofline["dp_in_place"] = dp_in_place
 
     e2e_launch = ("HostFedTrainer: cuda-graph step" + (" (NCCL all-reduce captured)" if dp is not None else "")
-                  + ", next batch H2D overlapped, loss read one step behind") if used_graph else "eager"
+                  + ", next batches' H2D overlapped, 8 buffer sets, each step's loss read up to 7 steps behind") if used_graph else "eager"
+    gc.enable()
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 unsampled=unsampled,
                 launches_per_step=launches_per_step, roofline=roofline, eval_info=eval_info,

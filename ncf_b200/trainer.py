@@ -222,8 +222,8 @@ class HostFedTrainer:
         hf = HostFedTrainer(ts, batch); hf.prefetch(*b[0])
         for k in range(n): hf.prefetch(*b[k + 1]); loss = hf.step()
 
-    `launch()` / `wait()` split the step so that the GPU never waits for the host: up to two steps may be in
-    flight, and `wait()` returns the loss of the oldest one (the reference only sums the losses for its log
+    `launch()` / `wait()` split the step so that the GPU never waits for the host: up to `depth` steps may be
+    staged or in flight, and `wait()` returns the loss of the oldest one (the reference only sums the losses for its log
     line, so reading step k's loss while step k+1 runs changes nothing):
 
         hf.prefetch(*b[0]); hf.launch(); hf.prefetch(*b[1])
@@ -231,20 +231,24 @@ class HostFedTrainer:
         loss = hf.wait()
     """
 
-    def __init__(self, ts: FusedTrainStep, batch: int, step_fn=None):
+    def __init__(self, ts: FusedTrainStep, batch: int, step_fn=None, depth: int = 2):
         """`step_fn`: the step each graph records (default ts.step); a ReplicatedDataParallel.step makes this
-        the host-fed trainer of a data-parallel rank (every rank must then call launch() in lock step)."""
+        the host-fed trainer of a data-parallel rank (every rank must then call launch() in lock step).
+        `depth`: buffer sets = steps that may be staged / in flight at once (2 hides the copies; more also rides
+        out host hiccups longer than a step — a 65 536-sample step is 0.4 ms)."""
+        if depth < 2:
+            raise _lib.NcfError("HostFedTrainer: depth must be at least 2")
         dev = ts.device
-        self.ts, self.batch = ts, batch
+        self.ts, self.batch, self.depth = ts, batch, depth
         self.bufs = [(torch.empty(batch, dtype=torch.int64, device=dev),
                       torch.empty(batch, dtype=torch.int64, device=dev),
-                      torch.empty(batch, dtype=torch.float32, device=dev)) for _ in range(2)]
+                      torch.empty(batch, dtype=torch.float32, device=dev)) for _ in range(depth)]
         for b in self.bufs:  # valid indices for the capture pass
             b[0].zero_(); b[1].zero_(); b[2].zero_()
         # each graph = clear the loss accumulator, the step, park the loss in the set's own device word: the
         # read-back then runs on its own stream and the next step does not queue behind a PCIe round trip
         base_step = step_fn or ts.step
-        self.loss_dev = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.loss_dev = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(depth)]
 
         def recorded(j):
             def fn(user, item, label):
@@ -255,23 +259,22 @@ class HostFedTrainer:
         self.graphs = [ts.capture(*b, batch, recorded(j)) for j, b in enumerate(self.bufs)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.read_stream = torch.cuda.Stream(device=dev)
-        self.stepped = [torch.cuda.Event(), torch.cuda.Event()]
-        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
-        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]
         for e in self.consumed:
             e.record()
-        self.host_loss = torch.zeros(2, dtype=torch.float64).pin_memory()
-        self.done = [torch.cuda.Event(), torch.cuda.Event()]   # loss of the step on buffer set j is in host_loss[j]
+        self.host_loss = torch.zeros(depth, dtype=torch.float64).pin_memory()
+        self.done = [torch.cuda.Event() for _ in range(depth)]   # loss of the step on buffer set j is in host_loss[j]
         self.n_staged = 0   # batches staged so far
         self.n_run = 0      # batches trained (launched) so far
         self.n_waited = 0   # losses handed back so far
 
     def prefetch(self, user: torch.Tensor, item: torch.Tensor, label: torch.Tensor) -> None:
-        if self.n_staged - self.n_run >= 2:
-            raise _lib.NcfError("HostFedTrainer: two batches are already staged")
+        if self.n_staged - self.n_run >= self.depth:
+            raise _lib.NcfError(f"HostFedTrainer: all {self.depth} buffer sets hold batches that have not run yet")
         if user.numel() != self.batch:
             raise _lib.NcfError("HostFedTrainer: batches must have the captured size")
-        j = self.n_staged & 1
+        j = self.n_staged % self.depth
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[j])
             self.bufs[j][0].copy_(user, non_blocking=True)
@@ -284,9 +287,9 @@ class HostFedTrainer:
         """Enqueues the step on the oldest staged batch and the read-back of its loss."""
         if self.n_run >= self.n_staged:
             raise _lib.NcfError("HostFedTrainer.step: no staged batch")
-        if self.n_run - self.n_waited >= 2:
-            raise _lib.NcfError("HostFedTrainer.launch: two steps are in flight, wait() for the older one first")
-        j = self.n_run & 1
+        if self.n_run - self.n_waited >= self.depth:
+            raise _lib.NcfError(f"HostFedTrainer.launch: {self.depth} steps are in flight, wait() for the oldest first")
+        j = self.n_run % self.depth
         cur = torch.cuda.current_stream()
         cur.wait_event(self.copied[j])
         self.graphs[j].replay()
@@ -301,7 +304,7 @@ class HostFedTrainer:
         """Loss of the oldest step whose loss has not been read yet (blocks until that step is complete)."""
         if self.n_waited >= self.n_run:
             raise _lib.NcfError("HostFedTrainer.wait: no step in flight")
-        j = self.n_waited & 1
+        j = self.n_waited % self.depth
         self.done[j].synchronize()
         self.n_waited += 1
         return float(self.host_loss[j])

@@ -96,8 +96,8 @@ def test_tf32_tower_mode_within_stated_tolerance():
     assert 0 < err < 2e-3, err
 
 
-@pytest.mark.parametrize("pipelined", [False, True])
-def test_host_fed_trainer_equals_eager_steps(pipelined):
+@pytest.mark.parametrize("depth", [0, 2, 3])
+def test_host_fed_trainer_equals_eager_steps(depth):
     """HostFedTrainer (graph-captured steps fed from pinned host batches through a copy stream)
     follows the same trajectory as eager FusedTrainStep.step on device batches — also with two steps in
     flight (the loss of step k read while step k+1 runs)."""
@@ -119,14 +119,15 @@ def test_host_fed_trainer_equals_eager_steps(pipelined):
     for u, i, y in batches:
         ta.step(u.to(dev), i.to(dev), y.to(dev))
         eager.append(ta.pop_loss())
-    hf = HostFedTrainer(tb, B)
+    pipelined = depth > 0
+    hf = HostFedTrainer(tb, B, depth=max(depth, 2))
     hf.prefetch(*batches[0])
     fed = []
     for k in range(T):
         hf.launch()
         if k + 1 < T:
             hf.prefetch(*batches[k + 1])
-        if not pipelined or hf.in_flight == 2:
+        if not pipelined or hf.in_flight == hf.depth:
             fed.append(hf.wait())
     while hf.in_flight:
         fed.append(hf.wait())
