@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(kThreads) ncf_small_tile_kernel(const TilePara
     for (int k = 0; k < L; ++k) {
       const int C = S::W(k), N = S::W(k + 1);
       float* w = wp; float* wt = wp + C * N; float* b = wp + 2 * C * N;
-      for (int i = tid; i < C * N; i += kThreads) {
-        const float v = __ldg(p.w[k] + i);
-        w[i] = v;
-        wt[(i % C) * N + i / C] = v;
-      }
+      // W_k: coalesced 16-byte loads straight into the row-major image; W_k^T: a second pass over the same
+      // (now L1-resident) words with the OUTPUT index fastest, so that the shared-memory stores of a warp fall
+      // into 32 different banks (one pass storing wt[c * N + n] for consecutive c put all 32 lanes on one bank)
+      const float4* src4 = reinterpret_cast<const float4*>(p.w[k]);
+      for (int i = tid; i < C * N / 4; i += kThreads) reinterpret_cast<float4*>(w)[i] = __ldg(src4 + i);
+      for (int j = tid; j < C * N; j += kThreads) wt[j] = __ldg(p.w[k] + (j % N) * C + j / N);
       for (int i = tid; i < N; i += kThreads) b[i] = __ldg(p.b[k] + i);
       q.w[k] = w; q.wt[k] = wt; q.b[k] = b;
       wp += 2 * C * N + N;
@@ -298,12 +299,10 @@ __global__ void __launch_bounds__(kThreads) ncf_small_tile_kernel(const TilePara
       float* din = (K & 1) ? dB : dA;                                                                               \
       float* dout = (K & 1) ? dA : dB;                                                                              \
       wgrad_part<C, N>(din, q.h[k], p.gt + p.w_off[k], lane, warp * (C / kWarps));                                  \
-      if (warp == 0) {                                           /* bias gradient: column sums of delta */          \
-        for (int n = lane; n < N; n += 32) {                                                                        \
-          float sum = 0.f;                                                                                          \
-          for (int s2 = 0; s2 < 32; ++s2) sum += din[s2 * (N + kPad) + n];                                          \
-          atomicAdd(p.gt + p.b_off[k] + n, sum);                                                                    \
-        }                                                                                                           \
+      if (lane < N) {                                            /* bias gradient: column sums of delta, */        \
+        float sum = 0.f;                                         /* eight samples per warp                */        \
+        for (int s2 = warp * (32 / kWarps); s2 < (warp + 1) * (32 / kWarps); ++s2) sum += din[s2 * (N + kPad) + lane]; \
+        atomicAdd(p.gt + p.b_off[k] + lane, sum);                                                                   \
       }                                                                                                             \
       __syncthreads();                                           /* every thread is done reading every row */     \
       if constexpr (k > 0) {                                                                                        \
@@ -349,7 +348,10 @@ namespace ncf {
 // factor_num 8, 1..3 tower layers, MLP / NeuMF (GMF has no tower: the generic kernel is a pure gather)
 bool small_eligible(const TileParams& p) {
   static const bool off = getenv("NCF_SMALL_DISABLE") != nullptr && getenv("NCF_SMALL_DISABLE")[0] == '1';
-  return !off && p.f == kF && p.type != NCF_GMF && p.L >= 1 && p.L <= 3;
+  if (off || p.f != kF || p.type == NCF_GMF || p.L < 1 || p.L > 3) return false;
+  for (int k = 0; k < p.L; ++k)
+    if (reinterpret_cast<uintptr_t>(p.w[k]) & 15) return false;   // weights are staged with 16-byte loads
+  return true;
 }
 
 int launch_small_forward(TileParams& p, cudaStream_t st) {
