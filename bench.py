@@ -443,6 +443,7 @@ def run_ours(args):
         "eval": st["eval_info"],
         "sampler": sampler,
         "small_config": small_config_run(dev) if extras else None,
+        "kd_config": kd_config_run(dev) if extras else None,
         "gpu_eager_reference": gpu_eager_reference_run(dev, hbm_peak) if extras else None,
         "unsampled_loop": st["unsampled"],
         "row_sharded": row_sharded,
@@ -1017,6 +1018,76 @@ def small_config_run(dev, epochs_steps: int = 2048):
     return {"workload": "NeuMF f=8 L=3, synthetic ml1m shape, batch 256, Adam, CUDA-graph windows of 64 steps",
             "samples_per_s": steps * B / (ms * 1e-3), "us_per_step": ms * 1e3 / steps, "steps": steps,
             "ng_sample_ms_per_epoch": sample_ms, "negatives_per_epoch": int(stream.P * 4)}
+
+
+def kd_config_run(dev, steps: int = 1024):
+    """BASELINE configs[2]: response distillation on the ML-1M shape at the reference batch 256 — frozen teacher
+    NeuMF f=64 L=3, student NeuMF f=8 L=2, alpha 0.5 (src/distillation/response.py:15-32, scripts/train_student.py:
+    131-160).  Ours: FusedTrainStep(teacher=...) in CUDA-graph windows of 64 steps (teacher forward + fused student
+    step with the KD term in the loss epilogue).  Beside it the reference's own ResponseDistillation + optim.Adam
+    under torch eager on this GPU (oracle/_ref; skipped when that directory is absent)."""
+    import torch
+    from ncf_b200.models import NCF
+    from ncf_b200.synth import SHAPES, make_interactions
+    from ncf_b200.trainer import EpochStream, FusedTrainStep
+    inter = make_interactions("ml1m", device=dev)
+    U, I = inter.user_num, inter.item_num
+    B, W = 256, 64
+    torch.manual_seed(0)
+    teacher = NCF(U, I, 64, 3, 0.0, "NeuMF-end").to(dev).eval()
+    student = NCF(U, I, 8, 2, 0.0, "NeuMF-end").to(dev)
+    ts = FusedTrainStep(student, "adam", 1e-3, max_batch=B, teacher=teacher, alpha=0.5)
+    stream = EpochStream(inter.pos_user, inter.pos_item, U, I, num_ng=4, seed=1)
+    stream.begin_epoch(0)
+    wu = torch.empty(W * B, dtype=torch.int64, device=dev)
+    wi = torch.empty(W * B, dtype=torch.int64, device=dev)
+    wl = torch.empty(W * B, dtype=torch.float32, device=dev)
+    stream.fill(0, W * B, wu, wi, wl)
+    for k in range(W):
+        ts.step(wu[k * B:(k + 1) * B], wi[k * B:(k + 1) * B], wl[k * B:(k + 1) * B])
+    graph = ts.capture(wu, wi, wl, B)
+    n_windows = max(1, steps // W)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for w in range(n_windows):
+        stream.fill((w + 1) * W * B, W * B, wu, wi, wl)
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"workload": "response distillation, teacher NeuMF f=64 L=3 -> student NeuMF f=8 L=2, synthetic ml1m shape, "
+                       "batch 256, alpha 0.5, Adam, CUDA-graph windows of 64 steps",
+           "samples_per_s": n_windows * W * B / (ms * 1e-3), "us_per_step": ms * 1e3 / (n_windows * W)}
+    del graph, ts
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is not None:
+        torch.manual_seed(0)
+        rt = ref.NCF(U, I, 64, 3, 0.0, "NeuMF-end").to(dev).eval()
+        rs = ref.NCF(U, I, 8, 2, 0.0, "NeuMF-end").to(dev)
+        kd = ref.response.ResponseDistillation(rt, rs, temperature=2.0, alpha=0.5)
+        kd.train()
+        opt = torch.optim.Adam(rs.parameters(), lr=1e-3)
+        batches = reference_batches(U, I, B, 8, dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 300
+        for k in range(30 + n):
+            if k == 30:
+                torch.cuda.synchronize()
+                e0.record()
+            u, i, y = batches[k % 8]
+            opt.zero_grad()
+            loss = kd(u, i, y)
+            loss.backward()
+            opt.step()
+            loss.item()
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1) / n
+        out["gpu_eager_reference"] = {"samples_per_s": B / (rms * 1e-3), "us_per_step": rms * 1e3, "steps": n,
+                                      "kind": "reference"}
+    return out
 
 
 def main():
