@@ -69,6 +69,15 @@ int forward_dispatch(TileParams& p, const NcfModel* m, void* workspace, int64_t 
     g_tile_path = 3;
     return launch_umma_forward(p, tower_passes(m), (float*)workspace, st);
   }
+  if (wide_eligible(p)) {
+    const int64_t need = wide_workspace_floats(p, p.B) * 4;
+    if (!workspace || workspace_bytes < need) {
+      set_error("forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+      return NCF_ERR_WORKSPACE;
+    }
+    g_tile_path = 5;
+    return launch_wide_forward(p, (float*)workspace, st);
+  }
   g_tile_path = mma_tile_rows(p) == 0 ? 1 : 2;
   if (mma_tile_rows(p) == 0) return launch_generic_forward(p, st);
   const int64_t need = mma_split_floats(p) * 4;
@@ -91,6 +100,11 @@ extern "C" int64_t ncf_forward_workspace_bytes(const NcfModel* m, int64_t B) {
   int64_t bytes = ncf::mma_tile_rows(p) ? ncf::align_up(ncf::mma_split_floats(p) * 4, 256) : 0;
   if (ncf::umma_eligible(p))
     bytes = std::max(bytes, ncf::align_up(ncf::umma_forward_workspace_floats(p, B) * 4, 256) + 256);
+  // any batch up to B may be passed with a workspace of this size: cover the small-batch path as well
+  TileParams ps = p;
+  ps.B = std::min<int64_t>(B, 2048);
+  if (ps.B > 0 && ncf::wide_eligible(ps))
+    bytes = std::max(bytes, ncf::align_up(ncf::wide_workspace_floats(ps, ps.B) * 4, 256));
   return bytes;
 }
 

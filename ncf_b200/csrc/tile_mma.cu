@@ -696,8 +696,14 @@ int mma_tile_rows(const TileParams& p_in) {
   if (p_in.type == NCF_GMF) return 0;          // no tower: the generic kernel is already a pure gather
   if (p_in.f < 8 || (p_in.f & (p_in.f - 1)) != 0) return 0;  // block shapes assume power-of-two widths
   TileParams p = p_in;
-  if (mma_smem_bytes<64>(p) <= kSmemLimit) return 64;
-  if (mma_smem_bytes<32>(p) <= kSmemLimit) return 32;
+  const bool fit64 = mma_smem_bytes<64>(p) <= kSmemLimit, fit32 = mma_smem_bytes<32>(p) <= kSmemLimit;
+  static const int forced = getenv("NCF_MMA_TILE_ROWS") ? atoi(getenv("NCF_MMA_TILE_ROWS")) : 0;  // tuning knob
+  if (forced == 64 && fit64) return 64;
+  if (forced == 32 && fit32) return 32;
+  // a batch that leaves most SMs idle with 64-row tiles (the reference's 256: 4 CTAs) runs on twice as many CTAs
+  if (fit32 && p.B > 0 && (p.B + 63) / 64 * 2 <= ncf::num_sms()) return 32;
+  if (fit64) return 64;
+  if (fit32) return 32;
   return 0;
 }
 

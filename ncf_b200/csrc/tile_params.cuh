@@ -95,6 +95,11 @@ bool small_eligible(const TileParams& p);
 int launch_small_forward(TileParams& p, cudaStream_t st);
 int launch_small_train(TileParams& p, cudaStream_t st);
 
+// wide towers at small batches, forward only: one launch per layer over many CTAs (tile_wide.cu)
+bool wide_eligible(const TileParams& p);  // reads p.B
+int64_t wide_workspace_floats(const TileParams& p, int64_t B);
+int launch_wide_forward(TileParams& p, float* ws, cudaStream_t st);
+
 // tcgen05 path (tile_umma.cu): large batches, tower widths that are power-of-two multiples of 32
 bool umma_eligible(const TileParams& p);  // reads p.B
 int64_t umma_forward_workspace_floats(const TileParams& p, int64_t B);

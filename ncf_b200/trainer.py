@@ -57,7 +57,10 @@ class FusedTrainStep:
         self.loss_accum = torch.zeros(1, dtype=torch.float64, device=dev)
         self.num_steps = 0
         self._refresh()
-        self.workspace = torch.empty(ops.train_workspace_bytes(self._m, self.max_batch),
+        # one scratch for the fused step and for plain student forwards (the distillation objectives outside the
+        # fused epilogue run forward -> loss -> backward)
+        self.workspace = torch.empty(max(ops.train_workspace_bytes(self._m, self.max_batch),
+                                         ops.forward_workspace_bytes(self._m, self.max_batch)),
                                      dtype=torch.uint8, device=dev)
         self.teacher_logits = (torch.empty(self.max_batch, dtype=torch.float32, device=dev)
                                if teacher is not None else None)

@@ -233,6 +233,40 @@ def test_one_launch_prepare_equals_mark_then_catch_up(model_type, f, L, B):
     assert int((ta.state.user_last_step[user.clamp(0, U - 1)[keep.to(dev())]] == t_now).sum()) > B // 2
 
 
+@pytest.mark.parametrize("model_type,f,L,B", [("NeuMF-end", 64, 3, 256), ("MLP", 16, 1, 33), ("NeuMF-end", 32, 2, 2048),
+                                               ("NeuMF-end", 16, 4, 700)])
+def test_small_batch_forward_of_wide_towers_matches_oracle(model_type, f, L, B):
+    """The layer-per-launch forward (tile_wide.cu: frozen teachers and scoring at small batches) against the
+    numpy oracle, incl. a short last tile, an out-of-range pair (NaN) and the one-user-many-candidates form."""
+    from ncf_b200 import _lib
+    from ncf_b200.metrics import evaluate
+    from ncf_b200.models import NCF
+    torch.manual_seed(13)
+    rng = np.random.default_rng(13)
+    U, I = 500, 400
+    model = NCF(U, I, f, L, 0.0, model_type).to(dev()).eval()
+    params = state_np(model)
+    u = rng.integers(0, U, B)
+    i = rng.integers(0, I, B)
+    ref = onp.forward(params, u, i, model_type)
+    ub, ib = u.copy(), i.copy()
+    ub[B // 2] = U                                   # out of range: NaN for that sample only
+    with torch.no_grad():
+        got = model(torch.from_numpy(ub).to(dev()), torch.from_numpy(ib).to(dev())).cpu().numpy()
+    assert _lib.load().ncf_last_tile_path() == 5, "the layer-per-launch forward did not run"
+    assert np.isnan(got[B // 2])
+    keep = np.arange(B) != B // 2
+    assert_close(got[keep], ref[keep], "logits")
+    # evaluation form: every user's candidates share the user index
+    n, C = 7, 50
+    users = rng.integers(0, U, n)
+    cands = rng.integers(0, I, (n, C))
+    res = evaluate(model, torch.from_numpy(users).to(dev()), torch.from_numpy(cands).to(dev()), 10)
+    assert _lib.load().ncf_last_tile_path() == 5
+    ref2 = onp.forward(params, np.repeat(users, C), cands.reshape(-1), model_type).reshape(n, C)
+    assert_close(res.scores.cpu().numpy(), ref2, "candidate scores")
+
+
 def test_kd_response_matches_reference():
     from ncf_b200.trainer import FusedTrainStep
     z, meta = load_golden("kd_response")
