@@ -22,27 +22,38 @@ __device__ __forceinline__ float bias_c2(const AdamConst& c, float s) {  // 1 / 
   return 1.f / sqrtf(-expm1f(s * c.ln_b2));
 }
 
-// Brings one element from "state after step `last`" to "state after step last+gap" under zero
-// gradient.  c1s / c2s hold the bias terms of steps last+1 .. last+min(gap, kMaxReplay).
+// Brings N elements of one row from "state after step `last`" to "state after step last+gap" under zero
+// gradient.  c1s / c2s hold the bias terms of steps last+1 .. last+min(gap, kMaxReplay).  The N chains are
+// independent and advance together, step by step: a row 160 steps behind is the critical path of a small-batch
+// step, and eight elements replayed one after the other were eight times that path.  Per element the arithmetic
+// is what it always was (an element with m = 0 subtracts exact zeros).
+template <int N>
+__device__ __forceinline__ void replay_zero_steps_n(float* p, float* m, float* v, int gap, const float* c1s,
+                                                    const float* c2s, const AdamConst& c) {
+  if (gap <= 0) return;
+  const int n = min(gap, kMaxReplay);
+  float mm[N], r[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { mm[i] = m[i]; r[i] = sqrtf(v[i]); }
+#pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    const float c1 = c1s[j], c2 = c2s[j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      mm[i] *= c.b1;
+      r[i] *= c.sqrt_b2;
+      p[i] -= c1 * __fdividef(mm[i], fmaf(r[i], c2, c.eps));
+    }
+  }
+  const float dm = expf((float)gap * c.ln_b1), dv = expf((float)gap * c.ln_b2);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { m[i] *= dm; v[i] *= dv; }
+}
+
 __device__ __forceinline__ void replay_zero_steps(float& p, float& m, float& v, int gap,
                                                   const float* c1s, const float* c2s,
                                                   const AdamConst& c) {
-  if (gap <= 0) return;
-  const int n = min(gap, kMaxReplay);
-  const float m0 = m, v0 = v;
-  float mm = m0, r = sqrtf(v0);
-  if (m0 != 0.f) {
-    // the terms are independent but for mm, r and the running p: unrolled, their table loads and reciprocals
-    // overlap (a row 160 steps behind is the critical path of a small-batch step)
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
-      mm *= c.b1;
-      r *= c.sqrt_b2;
-      p -= c1s[j] * __fdividef(mm, fmaf(r, c2s[j], c.eps));
-    }
-  }
-  m = m0 * expf((float)gap * c.ln_b1);
-  v = v0 * expf((float)gap * c.ln_b2);
+  replay_zero_steps_n<1>(&p, &m, &v, gap, c1s, c2s, c);
 }
 
 // The same replay with the bias terms evaluated on the fly (rows whose steps are not in a caller's table).

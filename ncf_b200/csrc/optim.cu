@@ -29,12 +29,16 @@ __device__ __forceinline__ void adam_row(float* __restrict__ P, float* __restric
       float4 v4 = *reinterpret_cast<float4*>(Vv + e);
       float4 g4 = make_float4(0, 0, 0, 0);
       if (G) g4 = *reinterpret_cast<float4*>(G + e);
-      float* pp = &p4.x; float* mp = &m4.x; float* vp = &v4.x; float* gp = &g4.x;
+      float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mp[4] = {m4.x, m4.y, m4.z, m4.w}, vp[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float* gp = &g4.x;
+      replay_zero_steps_n<4>(pp, mp, vp, gap, c1s, c2s, c);
+      if (G) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        replay_zero_steps(pp[q], mp[q], vp[q], gap, c1s, c2s, c);
-        if (G) adam_real_step(pp[q], mp[q], vp[q], gp[q], c1t, c2t, c);
+        for (int q = 0; q < 4; ++q) adam_real_step(pp[q], mp[q], vp[q], gp[q], c1t, c2t, c);
       }
+      p4 = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      m4 = make_float4(mp[0], mp[1], mp[2], mp[3]);
+      v4 = make_float4(vp[0], vp[1], vp[2], vp[3]);
       *reinterpret_cast<float4*>(P + e) = p4;
       *reinterpret_cast<float4*>(M + e) = m4;
       *reinterpret_cast<float4*>(Vv + e) = v4;
@@ -204,16 +208,19 @@ __device__ __forceinline__ void adam_rows_body(const RowsParams& q, const int64_
         c2s[j] = bias_c2(q.c, s);
       }
       __syncwarp();
-      float* a[8] = {&pg.x, &mg.x, &vg.x, &gg.x, &pm.x, &mm.x, &vm.x, &gm.x};
+      // the lane's eight elements (4 of the GMF row, 4 of the MLP row) replay together
+      float pe[8] = {pg.x, pg.y, pg.z, pg.w, pm.x, pm.y, pm.z, pm.w};
+      float me[8] = {mg.x, mg.y, mg.z, mg.w, mm.x, mm.y, mm.z, mm.w};
+      float ve[8] = {vg.x, vg.y, vg.z, vg.w, vm.x, vm.y, vm.z, vm.w};
+      replay_zero_steps_n<8>(pe, me, ve, gap, c1s, c2s, q.c);
+      if (kStep) {
+        const float ge[8] = {gg.x, gg.y, gg.z, gg.w, gm.x, gm.y, gm.z, gm.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        replay_zero_steps(a[0][k], a[1][k], a[2][k], gap, c1s, c2s, q.c);
-        replay_zero_steps(a[4][k], a[5][k], a[6][k], gap, c1s, c2s, q.c);
-        if (kStep) {
-          adam_real_step(a[0][k], a[1][k], a[2][k], a[3][k], c1t, c2t, q.c);
-          adam_real_step(a[4][k], a[5][k], a[6][k], a[7][k], c1t, c2t, q.c);
-        }
+        for (int k = 0; k < 8; ++k) adam_real_step(pe[k], me[k], ve[k], ge[k], c1t, c2t, q.c);
       }
+      pg = make_float4(pe[0], pe[1], pe[2], pe[3]); pm = make_float4(pe[4], pe[5], pe[6], pe[7]);
+      mg = make_float4(me[0], me[1], me[2], me[3]); mm = make_float4(me[4], me[5], me[6], me[7]);
+      vg = make_float4(ve[0], ve[1], ve[2], ve[3]); vm = make_float4(ve[4], ve[5], ve[6], ve[7]);
       if (lg) {
         *reinterpret_cast<float4*>(q.p_gmf[side] + og) = pg;
         *reinterpret_cast<float4*>(q.m_gmf[side] + og) = mg;
