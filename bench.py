@@ -751,8 +751,9 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
             du.copy_(hu[sl(k)]); di.copy_(hi[sl(k)]); dl.copy_(hl[sl(k)])
             step_fn(du, di, dl)
         barrier()
-        # at N>1 the exchange is captured too; 8 buffer sets: the host may fall 3 ms behind before the GPU idles
-        hf = HostFedTrainer(ts, B, step_fn if dp is not None else None, depth=8)
+        # at N>1 the exchange is captured too.  8 buffer sets on one GPU: the host may fall 3 ms behind before the
+        # GPU idles; at N>1 the two sets the multi-GPU runs of this round were measured with
+        hf = HostFedTrainer(ts, B, step_fn if dp is not None else None, depth=8 if dp is None else 2)
         nb = W + K
         hf.prefetch(hu[sl(0)], hi[sl(0)], hl[sl(0)])
 
@@ -957,7 +958,8 @@ def main_workload(args, dev, world, rank, local, hbm_peak, peak_src, K, W):
         roofline["dp_in_place"] = dp_in_place
 
     e2e_launch = ("HostFedTrainer: cuda-graph step" + (" (NCCL all-reduce captured)" if dp is not None else "")
-                  + ", next batches' H2D overlapped, 8 buffer sets, each step's loss read up to 7 steps behind") if used_graph else "eager"
+                  + f", next batches' H2D overlapped, {8 if dp is None else 2} buffer sets, each step's loss read up to "
+                  f"{7 if dp is None else 1} steps behind") if used_graph else "eager"
     gc.enable()
     return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, e2e_ms=e2e_ms, clocks=clocks, e2e_launch=e2e_launch,
                 unsampled=unsampled,
