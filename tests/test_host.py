@@ -239,3 +239,36 @@ def test_optimiser_mode_heuristic():
         assert ts.dense_adam(1)
     finally:
         del os.environ["NCF_ADAM_DENSE"]
+
+
+def test_distillation_fused_specs_describe_the_reference_objectives():
+    """What FusedTrainStep is told to run for each strategy (no device work): weights of the task / KD terms as
+    reference base.py:40-50, response.py:43-61, feature.py:138-146, attention.py:93-101 combine them, which
+    embedding-level features are matched (adapters where widths differ) and what is refused."""
+    from ncf_b200.distillation import (AttentionDistillation, FeatureDistillation, ResponseDistillation,
+                                       SoftTargetDistillation, UnifiedDistillation)
+    from ncf_b200.models import NCF
+    torch.manual_seed(0)
+    teacher = NCF(30, 20, 16, 4, 0.0, "NeuMF-end")     # the reference script's rule: (2f, L+1) of the student
+    student = NCF(30, 20, 8, 3, 0.0, "NeuMF-end")
+    r = ResponseDistillation(teacher, student, 2.0, 0.5).fused_spec()
+    assert (r["w_task"], r["w_kd"], r["kd_mode"], r["features"]) == (0.5, 0.5, 0, [])
+    s = SoftTargetDistillation(teacher, student).fused_spec()          # defaults T=4, alpha=0.7
+    assert s["kd_mode"] == 1 and s["temperature"] == 4.0 and abs(s["w_task"] - 0.7) < 1e-12 and abs(s["w_kd"] - 0.3) < 1e-12
+    fd = FeatureDistillation(teacher, student, 2.0, 0.5, 0.3)
+    assert sorted(fd.matched_keys()) == ["gmf_features", "mlp_input"]  # tower widths differ: skipped, as in the reference
+    f = fd.fused_spec()
+    assert abs(f["w_kd"] - 0.2) < 1e-12 and [x["kind"] for x in f["features"]] == [0, 1]
+    assert all(abs(x["weight"] - 0.15) < 1e-12 for x in f["features"])  # beta / number of matched features
+    assert tuple(f["features"][0]["w"].shape) == (16, 8) and tuple(f["features"][1]["w"].shape) == (256, 64)
+    a = AttentionDistillation(teacher, student, 2.0, 0.5, 0.2).fused_spec()
+    assert abs(a["w_kd"] - 0.3) < 1e-12 and a["features"] == []
+    u = UnifiedDistillation(teacher, student, 2.0, 0.4, 0.3, 0.2).fused_spec()
+    assert abs(u["w_kd"] - 0.1) < 1e-12 and len(u["features"]) == 2
+    assert all(not p.requires_grad for p in teacher.parameters())       # frozen (base.py:16-18)
+    # equal architectures: tower activations match as well -> only the autograd path serves that pair
+    twin = NCF(30, 20, 8, 3, 0.0, "NeuMF-end")
+    same = FeatureDistillation(twin, student, 2.0, 0.5, 0.3)
+    assert any(k.startswith("mlp_linear") for k in same.matched_keys())
+    with pytest.raises(NotImplementedError):
+        same.fused_spec()
